@@ -1,0 +1,175 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.json from the COMPILED REFERENCE (oracle/_ref/avx-ecm-ref).
+
+TEST INFRASTRUCTURE.  Runs only in the dev container (needs /root/reference to have
+been compiled by oracle/build_ref.sh).  For every case the unmodified reference binary is
+run with threads=1 and an explicit sigma in a scratch directory; we keep
+
+  * the save_b1.txt lines byte for byte                       (ecm.c:1372-1380)
+  * stage-1 Z and stage-2 accumulator of every lane, captured by the mpz_gcd LD_PRELOAD
+    tap (oracle/shim/gcd_tap.c) and taken out of Montgomery form (x * R^-1 mod N,
+    R = 2^MAXBITS as printed by main.c:529-533), i.e. the R-independent true residues
+  * the "found ... factor" reports                            (ecm.c:1356-1358,1510-1513)
+  * the op counters the reference prints                      (ecm.c:1849,1482, pairmap steps)
+
+Usage: python tools/gen_golden.py [case ...]
+"""
+import json, os, re, subprocess, sys, tempfile, random
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "avx-ecm-ref")
+TAP = os.path.join(ROOT, "oracle", "_ref", "gcd_tap.so")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def is_prime(n, rounds=24):
+    if n < 2:
+        return False
+    for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if n % p == 0:
+            return n == p
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    rng = random.Random(n & 0xFFFFFFFF)
+    for _ in range(rounds):
+        a = rng.randrange(2, n - 1)
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def next_prime(n):
+    n |= 1
+    while not is_prime(n):
+        n += 2
+    return n
+
+
+def synthetic(bits_p, bits_q, seed):
+    """N = p*q, p,q = next primes after seeded random odd numbers with the top bit set."""
+    rng = random.Random(seed)
+    p = next_prime(rng.getrandbits(bits_p) | (1 << (bits_p - 1)) | 1)
+    q = next_prime(rng.getrandbits(bits_q) | (1 << (bits_q - 1)) | 1)
+    return p * q
+
+
+def fib(n):
+    a, b = 0, 1
+    for _ in range(n):
+        a, b = b, a + b
+    return a
+
+
+def composites():
+    return {
+        "syn415": synthetic(207, 208, 12345),     # 415 bits -> NWORDS=8 class
+        "syn1024": synthetic(512, 512, 12346),
+        "syn2048": synthetic(1024, 1024, 12347),
+        "readme508": fib(791) // 13 // 677 // 216416017,
+        "t35": 142946323174762557214361604817789197531833590620956958433836799929503392464892596183803921,
+        "csh250k": 171527316193270871507108435893460246746982712299171622350010323023149618461701108180621787596877308885636902619030669,
+        "csh1m": 7908926676514675413083853032827063880118980193445471625562601469958414706043143581401715516956542424923236530406833110566233,
+        "small96": 1000000007 * 998244353 * 4294967311,   # tiny composite: exercises factor/inversion-failure paths
+    }
+
+
+def cases():
+    c = composites()
+    return [
+        # name, N, curves, B1, B2, sigma0
+        ("readme508_b1_5e4", c["readme508"], 8, 50000, 5000000, 1000),
+        ("syn415_b1_1e5", c["syn415"], 8, 100000, 10000000, 7),
+        ("syn415_b1_3e4_s1only", c["syn415"], 16, 30000, 30000, 100),
+        ("syn1024_b1_2e4", c["syn1024"], 8, 20000, 2000000, 7),
+        ("syn2048_b1_5e3", c["syn2048"], 8, 5000, 500000, 7),
+        ("csh250k_stage1_factor", c["csh250k"], 8, 250000, 250000, 3462348953),
+        ("csh1m_stage1_factor", c["csh1m"], 8, 1000000, 1000000, 7372562557),
+        ("t35_stage2_factor", c["t35"], 8, 1000000, 100000000, 416265588),
+        ("t35_b1_2e4_sigma64", c["t35"], 8, 20000, 2000000, 11919771003873180376),
+        ("small96_D1155", c["small96"], 8, 3000, 300000, 11),
+        ("small96_D385", c["small96"], 8, 1500, 150000, 11),
+        ("small96_D210", c["small96"], 8, 400, 40000, 11),
+        ("small96_D120", c["small96"], 8, 200, 20000, 11),
+        ("small96_D60", c["small96"], 8, 100, 10000, 11),
+        ("small96_D30", c["small96"], 8, 50, 5000, 11),
+        ("syn415_two_ranges", c["syn415"], 8, 2000, 100100000, 7),   # B2 spans two 1e8 prime ranges
+    ]
+
+
+def run_case(name, N, curves, B1, B2, sigma0):
+    with tempfile.TemporaryDirectory() as d:
+        tap = os.path.join(d, "tap.log")
+        env = dict(os.environ, GCD_TAP_FILE=tap, LD_PRELOAD=TAP)
+        out = subprocess.run([REF, str(N), str(curves), str(B1), "1", str(B2), str(sigma0)],
+                             cwd=d, env=env, capture_output=True, text=True, check=True).stdout
+        save = open(os.path.join(d, "save_b1.txt")).read().splitlines(keepends=True)
+        taps = [l.split()[1:] for l in open(tap).read().splitlines()]
+    maxbits = int(re.search(r"Choosing MAXBITS = (\d+)", out).group(1))
+    Rinv = pow(1 << maxbits, -1, N)
+    do2 = B2 > B1
+    nb = len(save) // 8                      # batches actually run (stops after a find, ecm.c:1531)
+    # gcd calls per batch: 8 x stage-1 Z, [inversion failures...], 8 x stage-2 acc (all with b == N)
+    z1, acc, inv_fail_operands = [], [], []
+    calls = [(int(a, 16), int(b, 16)) for a, b in taps if int(b, 16) == N]
+    per = []
+    # split calls into batches: the reference processes batches sequentially
+    idx = 0
+    for b in range(nb):
+        z1 += [a * Rinv % N for a, _ in calls[idx:idx + 8]]
+        idx += 8
+        if do2:
+            # everything up to the last 8 calls of this batch are inversion-failure gcds
+            nxt = idx
+            # count failure gcds: total calls minus 16 per batch when only one batch; for
+            # several batches we rely on the run stopping at the first find.
+            remaining = len(calls) - idx - 8 - (nb - b - 1) * 16
+            inv_fail_operands += [hex(a) for a, _ in calls[idx:idx + remaining]]
+            idx += remaining
+            acc += [a * Rinv % N for a, _ in calls[idx:idx + 8]]
+            idx += 8
+    factors = []
+    for m in re.finditer(r"found \S+ factor (\d+) in stage (\d) \(B\d = \d+\): thread 0, vec (\d+), sigma (\d+)", out):
+        factors.append({"factor": m.group(1), "stage": int(m.group(2)), "lane": int(m.group(3)), "sigma": m.group(4)})
+    cnt = {}
+    m = re.search(r"with (\d+) point-adds and (\d+) point-doubles", out)
+    cnt["s1_ptadds"], cnt["s1_ptdups"] = int(m.group(1)), int(m.group(2))
+    if do2:
+        m = re.search(r"performed (\d+) pt-adds, (\d+) inversions, and (\d+) pair-muls", out)
+        cnt["s2_ptadds"], cnt["s2_numinv"], cnt["s2_paired"] = map(int, m.groups())
+        cnt["pairmap_steps"] = sum(int(x) for x in re.findall(r"pairmap step 0 of (\d+)", out))
+        m = re.search(r"w = (\d+), R = (\d+), L = (\d+), U = (\d+)", out)
+        cnt["D"], cnt["R"], cnt["L"], cnt["U"] = map(int, m.groups())
+    return {
+        "name": name, "n": str(N), "curves_requested": curves, "b1": B1, "b2": B2, "sigma0": str(sigma0),
+        "maxbits_ref": maxbits, "save_lines": save,
+        "z1_true_hex": [hex(x)[2:] for x in z1], "acc_true_hex": [hex(x)[2:] for x in acc],
+        "inv_fail_gcd_calls": len(inv_fail_operands),
+        "factors": factors, "counts": cnt,
+    }
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    comp = {k: str(v) for k, v in composites().items()}
+    json.dump(comp, open(os.path.join(OUT, "composites.json"), "w"), indent=1)
+    want = set(sys.argv[1:])
+    for c in cases():
+        if want and c[0] not in want:
+            continue
+        g = run_case(*c)
+        json.dump(g, open(os.path.join(OUT, c[0] + ".json"), "w"), indent=1)
+        print(c[0], "lanes", len(g["save_lines"]), "factors", [(f["sigma"], f["stage"], f["factor"]) for f in g["factors"]],
+              g["counts"], "invfail", g["inv_fail_gcd_calls"], flush=True)
+
+
+if __name__ == "__main__":
+    main()
