@@ -1,0 +1,260 @@
+"""avx-ecm_b200: B200-native engine for avx-ecm's hot path (batched Montgomery arithmetic ->
+stage 1 PRAC -> stage 2 pairing), reached through the C ABI in include/ecm_b200.h.
+
+This module is the thin Python host layer over libecm_b200.so (ctypes).  It mirrors the
+reference's driver vocabulary (vececm / ecm_stage1 / save_b1.txt lines, ecm.c:1077-1544) so that
+tests read like the reference's own runs.  There is NO CPU fallback: if the CUDA library is
+missing or no GPU is present the calls raise.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.realpath(__file__))
+LIB_PATH = os.path.join(_HERE, "libecm_b200.so")
+_lib = None
+
+u8p = ctypes.POINTER(ctypes.c_uint8)
+u32p = ctypes.POINTER(ctypes.c_uint32)
+u64p = ctypes.POINTER(ctypes.c_uint64)
+
+
+class EcmError(RuntimeError):
+    pass
+
+
+def build(limbs=None, force=False):
+    """Compile libecm_b200.so in-tree with nvcc for sm_100a (no GPU needed to compile)."""
+    cmd = ["make", "-C", _HERE]
+    if limbs:
+        cmd.append("LIMBS=" + limbs)
+    if force:
+        subprocess.run(["make", "-C", _HERE, "clean"], check=True, capture_output=True)
+    subprocess.run(cmd, check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EcmError("libecm_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                       "there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp = c.c_void_p
+    sig = {
+        "ecm_b200_create": (c.c_int, [c.POINTER(vp), c.c_int, u32p, c.c_int, c.c_uint32]),
+        "ecm_b200_destroy": (None, [vp]),
+        "ecm_b200_last_error": (c.c_char_p, []),
+        "ecm_b200_limbs": (c.c_int, [vp]),
+        "ecm_b200_build_curves": (c.c_int, [vp, c.c_uint32, u64p]),
+        "ecm_b200_load_curves": (c.c_int, [vp, c.c_uint32, u32p, u32p]),
+        "ecm_b200_stage1": (c.c_int, [vp, c.c_uint64]),
+        "ecm_b200_stage1_begin": (c.c_int, [vp, c.c_uint64]),
+        "ecm_b200_stage1_step": (c.c_int, [vp, c.c_uint32, c.POINTER(c.c_int)]),
+        "ecm_b200_stage1_launches": (c.c_int, [vp, u32p, u32p]),
+        "ecm_b200_sync": (c.c_int, [vp]),
+        "ecm_b200_read_stage1": (c.c_int, [vp, u32p, u32p, u8p, u32p]),
+        "ecm_b200_stage2": (c.c_int, [vp, c.c_uint64, c.c_uint64]),
+        "ecm_b200_read_stage2": (c.c_int, [vp, u32p, u8p, u32p, u8p]),
+        "ecm_b200_plan_stage1": (c.c_uint64, [c.c_uint64, u8p, c.c_uint64, u64p]),
+        "ecm_b200_pair": (c.c_uint32, [c.c_uint64, c.c_uint64, c.c_uint32, c.c_uint32, u32p, u32p, c.c_uint32, u32p, u32p]),
+        "ecm_b200_stage2_params": (None, [c.c_uint64, u32p, u32p, u32p, u32p]),
+        "ecm_b200_fieldop": (c.c_int, [vp, c.c_int, c.c_uint32, u32p, u32p, u32p, c.c_int]),
+        "ecm_b200_launch_count": (c.c_uint64, []),
+        "ecm_b200_last_timing": (c.c_int, [vp, c.POINTER(c.c_float), u32p]),
+        "ecm_b200_measure_imad_peak": (c.c_int, [c.c_int, c.POINTER(c.c_double), c.POINTER(c.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTS = ["ecm_b200_create", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
+           "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
+           "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_read_stage1", "ecm_b200_stage2",
+           "ecm_b200_read_stage2", "ecm_b200_plan_stage1", "ecm_b200_pair", "ecm_b200_stage2_params",
+           "ecm_b200_fieldop", "ecm_b200_launch_count", "ecm_b200_last_timing", "ecm_b200_measure_imad_peak"]
+
+
+def _check(rc):
+    if rc != 0:
+        raise EcmError("ecm_b200 error %d: %s" % (rc, lib().ecm_b200_last_error().decode()))
+
+
+# ---- limb packing: batch buffers are [limb][curve] uint32 (include/ecm_b200.h) ---------------------
+def pack(values, nl):
+    n = len(values)
+    buf = (ctypes.c_uint32 * (nl * n))()
+    for i, v in enumerate(values):
+        for k in range(nl):
+            buf[k * n + i] = (v >> (32 * k)) & 0xFFFFFFFF
+    return buf
+
+
+def unpack(buf, nl, n):
+    out = []
+    for i in range(n):
+        v = 0
+        for k in range(nl):
+            v |= buf[k * n + i] << (32 * k)
+        out.append(v)
+    return out
+
+
+def save_line(sigma, b1, N, x, z):
+    """One save_b1.txt line, byte for byte what the reference appends (ecm.c:1372-1380)."""
+    return "METHOD=ECM; SIGMA=%d; B1=%d; N=0x%x; X=0x%x; Z=0x%x; PROGRAM=AVX-ECM;\n" % (sigma, b1, N, x, z)
+
+
+class EcmContext:
+    """One batch of curves sharing N on one GPU (the analogue of the reference's thread_data_t[],
+    avx_ecm.h:265-287; one context per GPU replaces one pthread per 8 lanes)."""
+
+    def __init__(self, N, max_curves, device=0):
+        L = lib()
+        self.N = N
+        nlimbs = max(1, (N.bit_length() + 31) // 32)
+        nbuf = (ctypes.c_uint32 * nlimbs)(*[(N >> (32 * k)) & 0xFFFFFFFF for k in range(nlimbs)])
+        self._h = ctypes.c_void_p()
+        _check(L.ecm_b200_create(ctypes.byref(self._h), device, nbuf, nlimbs, max_curves))
+        self.nl = L.ecm_b200_limbs(self._h)
+        self.max_curves = max_curves
+        self.count = 0
+        self.sigmas = []
+
+    def close(self):
+        if self._h:
+            lib().ecm_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # phase 0 (build_one_curve, ecm.c:1548-1803)
+    def build_curves(self, sigmas):
+        s = (ctypes.c_uint64 * len(sigmas))(*sigmas)
+        _check(lib().ecm_b200_build_curves(self._h, len(sigmas), s))
+        self.count, self.sigmas = len(sigmas), list(sigmas)
+
+    def load_curves(self, xs, ss, sigmas=None):
+        _check(lib().ecm_b200_load_curves(self._h, len(xs), pack(xs, self.nl), pack(ss, self.nl)))
+        self.count, self.sigmas = len(xs), list(sigmas or range(len(xs)))
+
+    # phase 1 (ecm_stage1, ecm.c:1806-1854)
+    def stage1(self, b1):
+        _check(lib().ecm_b200_stage1(self._h, b1))
+        self.b1 = b1
+
+    def stage1_begin(self, b1):
+        _check(lib().ecm_b200_stage1_begin(self._h, b1))
+        self.b1 = b1
+
+    def stage1_step(self, max_launches):
+        done = ctypes.c_int(0)
+        _check(lib().ecm_b200_stage1_step(self._h, max_launches, ctypes.byref(done)))
+        return bool(done.value)
+
+    def stage1_launches(self):
+        t, i = ctypes.c_uint32(), ctypes.c_uint32()
+        _check(lib().ecm_b200_stage1_launches(self._h, ctypes.byref(t), ctypes.byref(i)))
+        return t.value, i.value
+
+    def sync(self):
+        _check(lib().ecm_b200_sync(self._h))
+
+    def read_stage1(self):
+        """-> (X, Z, factors): residues as written to save_b1.txt and gcd(Z,N) when it is a proper factor."""
+        n, nl = self.count, self.nl
+        x = (ctypes.c_uint32 * (nl * n))()
+        z = (ctypes.c_uint32 * (nl * n))()
+        g = (ctypes.c_uint32 * (nl * n))()
+        fl = (ctypes.c_uint8 * n)()
+        _check(lib().ecm_b200_read_stage1(self._h, x, z, fl, g))
+        gs = unpack(g, nl, n)
+        return unpack(x, nl, n), unpack(z, nl, n), [gs[i] if fl[i] else 0 for i in range(n)]
+
+    # phases 2+3 (ecm_stage2_init / ecm_stage2_pair, ecm.c:2201-2540)
+    def stage2(self, b1, b2):
+        _check(lib().ecm_b200_stage2(self._h, b1, b2))
+
+    def read_stage2(self):
+        n, nl = self.count, self.nl
+        acc = (ctypes.c_uint32 * (nl * n))()
+        g = (ctypes.c_uint32 * (nl * n))()
+        fl = (ctypes.c_uint8 * n)()
+        iv = (ctypes.c_uint8 * n)()
+        _check(lib().ecm_b200_read_stage2(self._h, acc, fl, g, iv))
+        gs = unpack(g, nl, n)
+        return unpack(acc, nl, n), [gs[i] if fl[i] else 0 for i in range(n)], list(iv)
+
+    def fieldop(self, op, a, b, repeat=1):
+        n, nl = len(a), self.nl
+        r = (ctypes.c_uint32 * (nl * n))()
+        _check(lib().ecm_b200_fieldop(self._h, op, n, pack(a, nl), pack(b, nl), r, repeat))
+        return unpack(r, nl, n)
+
+    def last_timing(self):
+        ms, ln = ctypes.c_float(), ctypes.c_uint32()
+        _check(lib().ecm_b200_last_timing(self._h, ctypes.byref(ms), ctypes.byref(ln)))
+        return ms.value, ln.value
+
+
+def plan_stage1(b1):
+    """-> (ops bytes, point adds, point doublings) for B1 (prac planner, ecm.c:479-884,1815-1832)."""
+    L = lib()
+    cnt = (ctypes.c_uint64 * 2)()
+    n = L.ecm_b200_plan_stage1(b1, None, 0, cnt)
+    buf = (ctypes.c_uint8 * max(1, n))()
+    L.ecm_b200_plan_stage1(b1, buf, n, cnt)
+    return bytes(buf[:n]), cnt[0], cnt[1]
+
+
+def pair(lo, hi, D, U=16):
+    L = lib()
+    amin, npairs = ctypes.c_uint32(), ctypes.c_uint32()
+    steps = L.ecm_b200_pair(lo, hi, D, U, None, None, 0, ctypes.byref(amin), ctypes.byref(npairs))
+    v = (ctypes.c_uint32 * max(1, steps))()
+    u = (ctypes.c_uint32 * max(1, steps))()
+    L.ecm_b200_pair(lo, hi, D, U, v, u, steps, ctypes.byref(amin), ctypes.byref(npairs))
+    return list(v[:steps]), list(u[:steps]), amin.value, npairs.value
+
+
+def stage2_params(b1):
+    L = lib()
+    D, U, Lw, R = (ctypes.c_uint32() for _ in range(4))
+    L.ecm_b200_stage2_params(b1, ctypes.byref(D), ctypes.byref(U), ctypes.byref(Lw), ctypes.byref(R))
+    return D.value, U.value, Lw.value, R.value
+
+
+def vececm(N, curves, b1, b2=None, sigma=7, device=0, ctx=None):
+    """Driver for one batch, mirroring vececm() (ecm.c:1077-1544) with threads=1 semantics:
+    curve i runs sigma+i (main.c:757-763).  Returns dict(save_lines, factors=[(sigma, stage, factor)],
+    x, z, acc)."""
+    own = ctx is None
+    if own:
+        ctx = EcmContext(N, curves, device)
+    try:
+        sig = [sigma + i for i in range(curves)]
+        ctx.build_curves(sig)
+        ctx.stage1(b1)
+        x, z, f1 = ctx.read_stage1()
+        out = {"save_lines": [save_line(s, b1, N, xi, zi) for s, xi, zi in zip(sig, x, z)],
+               "factors": [(s, 1, f) for s, f in zip(sig, f1) if f], "x": x, "z": z, "acc": None}
+        if b2 is None:
+            b2 = 100 * b1                       # main.c:462
+        if b2 > b1:                             # main.c:548-552
+            ctx.stage2(b1, b2)
+            acc, f2, inv_fail = ctx.read_stage2()
+            out["acc"], out["inv_fail"] = acc, inv_fail
+            out["factors"] += [(s, 2, f) for s, f in zip(sig, f2) if f]
+        return out
+    finally:
+        if own:
+            ctx.close()

@@ -1,0 +1,395 @@
+// ecm_gpu.cu -- C ABI of libecm_b200.so (include/ecm_b200.h): context, launch scheduling and
+// the host<->device plumbing.  No CPU fallback: without a usable CUDA device every entry point
+// fails with ECM_B200_ENODEV.
+#include "../../include/ecm_b200.h"
+#include "engine.hpp"
+#include "plan.hpp"
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ecmb200;
+enum { NSLOT_S1 = 13, SP = 12 };   // slot file of the stage-1 machine (vm.cuh)
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ECM_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+// ---- tiny host big-number helpers (little-endian 32-bit limbs, fixed length) -------------------
+int cmp(const Big &a, const Big &b)
+{
+    for (size_t i = a.size(); i-- > 0;) if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+    return 0;
+}
+uint32_t add_in(Big &a, const Big &b)
+{
+    uint64_t c = 0;
+    for (size_t i = 0; i < a.size(); i++) { c += (uint64_t)a[i] + b[i]; a[i] = (uint32_t)c; c >>= 32; }
+    return (uint32_t)c;
+}
+void sub_in(Big &a, const Big &b)
+{
+    int64_t c = 0;
+    for (size_t i = 0; i < a.size(); i++) { c += (int64_t)a[i] - b[i]; a[i] = (uint32_t)c; c >>= 32; }
+}
+void dbl_mod(Big &x, const Big &n)       // x = 2x mod n
+{
+    uint32_t top = x.back() >> 31;
+    for (size_t i = x.size(); i-- > 0;) x[i] = (x[i] << 1) | (i ? x[i - 1] >> 31 : 0);
+    if (top || cmp(x, n) >= 0) sub_in(x, n);
+}
+void half_mod(Big &x, const Big &n)      // x = x/2 mod n (n odd)
+{
+    uint32_t carry = 0;
+    if (x[0] & 1) carry = add_in(x, n);
+    for (size_t i = 0; i < x.size(); i++) x[i] = (x[i] >> 1) | ((i + 1 < x.size() ? x[i + 1] : carry) << 31);
+}
+uint32_t bitlen(const Big &x)
+{
+    for (size_t i = x.size(); i-- > 0;) if (x[i]) return (uint32_t)(32 * i + 32 - __builtin_clz(x[i]));
+    return 0;
+}
+
+// ---- engines: one translation unit per compiled limb count (engine_inst.cu) ---------------------
+#ifndef ECM_B200_LIMB_SET
+#error "ECM_B200_LIMB_SET must list the compiled limb counts, e.g. X(13) X(32)"
+#endif
+}  // namespace
+namespace ecmb200 {
+#define X(n) Engine *make_engine_##n();
+ECM_B200_LIMB_SET
+#undef X
+void count_launch() { g_launches++; }
+}
+namespace {
+Engine *make_engine(int nlimbs)
+{
+#define X(n) if (nlimbs <= n) return make_engine_##n();
+    ECM_B200_LIMB_SET
+#undef X
+    return nullptr;
+}
+
+}  // namespace
+
+struct ecm_b200_ctx {
+    int device = 0;
+    Engine *eng = nullptr;
+    int nl = 0;                 // engine limbs
+    Big n;                      // modulus padded to nl limbs
+    uint32_t max_curves = 0, cap = 0, count = 0, groups = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t *d_state = nullptr;
+    size_t state_words = 0;
+    uint8_t *d_ops = nullptr; size_t d_ops_cap = 0;
+    uint32_t *d_io = nullptr; size_t d_io_words = 0;     // staging for host<->device transfers
+    void *d_params = nullptr;
+    uint8_t *d_flags = nullptr;
+    Stage1Plan plan;            // cached for plan.b1
+    bool plan_on_device = false;
+    // stage-1 schedule
+    uint32_t chunk_len = 0; uint64_t total_items = 0, next_item = 0; uint32_t launches_total = 0, launches_issued = 0;
+    int p_slot = 0;             // physical point slot holding P
+    bool have_curves = false, stage1_done = false;
+    float last_ms = 0; uint32_t last_launches = 0;
+};
+
+extern "C" {
+
+const char *ecm_b200_last_error(void) { return g_err.c_str(); }
+uint64_t ecm_b200_launch_count(void) { return g_launches.load(); }
+int ecm_b200_limbs(const ecm_b200_ctx *ctx) { return ctx ? ctx->nl : 0; }
+
+int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimbs, uint32_t max_curves)
+{
+    if (!out || !n || nlimbs < 1 || max_curves < 1) return fail(ECM_B200_EINVAL, "bad argument");
+    *out = nullptr;
+    while (nlimbs > 1 && n[nlimbs - 1] == 0) nlimbs--;
+    if (!(n[0] & 1) || (nlimbs == 1 && n[0] < 3)) return fail(ECM_B200_EINVAL, "modulus must be odd and > 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+        return fail(ECM_B200_ENODEV, "no usable CUDA device (this engine has no CPU fallback)");
+    Engine *eng = make_engine(nlimbs);
+    if (!eng) return fail(ECM_B200_EINVAL, "modulus too large: kernels are built for up to 1024 bits (32 limbs)");
+    ecm_b200_ctx *c = new ecm_b200_ctx();
+    c->device = device; c->eng = eng; c->nl = eng->nl; c->max_curves = max_curves;
+    const int nl = c->nl;
+    c->n.assign(nl, 0);
+    for (int i = 0; i < nlimbs; i++) c->n[i] = n[i];
+    // Montgomery constants for R = 2^(32*nl)  (main.c:624-640 does this with GMP for R = 2^MAXBITS)
+    Big one(nl, 0); one[0] = 1;
+    for (int i = 0; i < 32 * nl; i++) dbl_mod(one, c->n);          // R mod N
+    Big r2 = one; for (int i = 0; i < 32 * nl; i++) dbl_mod(r2, c->n);
+    Big r3 = r2; for (int i = 0; i < 32 * nl; i++) dbl_mod(r3, c->n);
+    // reference R: MAXBITS = smallest multiple of 208 strictly above bitlen(N) (main.c:465-483)
+    uint32_t maxbits_ref = 208; while (maxbits_ref <= bitlen(c->n)) maxbits_ref += 208;
+    Big rri = one; for (uint32_t i = 0; i < maxbits_ref; i++) half_mod(rri, c->n);   // R * 2^-MAXBITS mod N
+    uint32_t inv = 1; for (int i = 0; i < 5; i++) inv *= 2 - c->n[0] * inv;           // N^-1 mod 2^32
+    const uint32_t m0inv = 0u - inv;
+    eng->set_params(c->n, one, r2, r3, rri, m0inv);
+
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e_); ecm_b200_destroy(c); return fail(ECM_B200_ECUDA, m); } } while (0)
+    CUC(cudaSetDevice(device));
+    CUC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CUC(eng->prepare());
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->ev0)); CUC(cudaEventCreate(&c->ev1));
+    const uint32_t T = eng->threads_s1;
+    c->cap = (max_curves + T - 1) / T * T;
+    c->state_words = (size_t)NSLOT_S1 * nl * c->cap;
+    CUC(cudaMalloc(&c->d_state, c->state_words * 4));
+    CUC(cudaMemsetAsync(c->d_state, 0, c->state_words * 4, c->stream));
+    c->d_io_words = (size_t)4 * nl * c->cap;
+    CUC(cudaMalloc(&c->d_io, c->d_io_words * 4));
+    CUC(cudaMalloc(&c->d_flags, (size_t)c->cap * 2));
+    CUC(cudaMalloc(&c->d_params, eng->params_bytes));
+    CUC(cudaMemcpyAsync(c->d_params, eng->params_host(), eng->params_bytes, cudaMemcpyHostToDevice, c->stream));
+    eng->set_params_device(c->d_params);
+    CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+    *out = c;
+    return ECM_B200_OK;
+}
+
+void ecm_b200_destroy(ecm_b200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_state); cudaFree(c->d_ops); cudaFree(c->d_io); cudaFree(c->d_flags); cudaFree(c->d_params);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c->eng;
+    delete c;
+}
+
+static int set_count(ecm_b200_ctx *c, uint32_t count)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (count < 1 || count > c->max_curves) return fail(ECM_B200_EINVAL, "count exceeds the context's max_curves");
+    c->count = count;
+    const uint32_t T = c->eng->threads_s1;
+    c->groups = (count + T - 1) / T;
+    c->have_curves = true; c->stage1_done = false; c->p_slot = 0;
+    c->total_items = c->next_item = 0; c->launches_total = c->launches_issued = 0;
+    return ECM_B200_OK;
+}
+
+int ecm_b200_load_curves(ecm_b200_ctx *c, uint32_t count, const uint32_t *x, const uint32_t *s)
+{
+    if (!c || !x || !s) return fail(ECM_B200_EINVAL, "null argument");
+    int rc = set_count(c, count); if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    const size_t words = (size_t)c->nl * count;
+    CU(cudaMemcpyAsync(c->d_io, x, words * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_io + words, s, words * 4, cudaMemcpyHostToDevice, c->stream));
+    c->eng->load_curves(c->stream, c->d_state, c->cap, count, c->d_io, c->d_io + words);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return ECM_B200_OK;
+}
+
+int ecm_b200_build_curves(ecm_b200_ctx *c, uint32_t count, const uint64_t *sigma)
+{
+    if (!c || !sigma) return fail(ECM_B200_EINVAL, "null argument");
+    int rc = set_count(c, count); if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    // u = sigma^2 - 5, v = 4 sigma (ecm.c:1587-1598), reduced mod N when N is below 2^128
+    std::vector<uint32_t> uv((size_t)8 * count);
+    unsigned __int128 nsmall = 0; bool small = bitlen(c->n) <= 127;
+    if (small) for (int i = 3; i >= 0; i--) nsmall = (nsmall << 32) | (i < c->nl ? c->n[i] : 0);
+    for (uint32_t i = 0; i < count; i++) {
+        if (sigma[i] < 6) return fail(ECM_B200_EINVAL, "sigma must be >= 6");
+        unsigned __int128 u = (unsigned __int128)sigma[i] * sigma[i] - 5, v = (unsigned __int128)sigma[i] * 4;
+        if (small) { u %= nsmall; v %= nsmall; }
+        for (int k = 0; k < 4; k++) { uv[(size_t)k * count + i] = (uint32_t)(u >> (32 * k)); uv[(size_t)(4 + k) * count + i] = (uint32_t)(v >> (32 * k)); }
+    }
+    if ((size_t)8 * count > c->d_io_words) return fail(ECM_B200_ENOMEM, "staging buffer too small");
+    CU(cudaMemcpyAsync(c->d_io, uv.data(), uv.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    c->eng->build_curves(c->stream, c->d_state, c->cap, count, c->d_io, c->d_flags);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return ECM_B200_OK;
+}
+
+int ecm_b200_stage1_begin(ecm_b200_ctx *c, uint64_t b1)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (!c->have_curves) return fail(ECM_B200_ESTATE, "no curves loaded");
+    if (b1 < 2 || b1 > 4000000000ull) return fail(ECM_B200_EINVAL, "B1 out of range");
+    CU(cudaSetDevice(c->device));
+    if (c->plan.b1 != b1) { plan_stage1(b1, c->plan); c->plan_on_device = false; }
+    if (!c->plan_on_device) {
+        if (c->plan.ops.size() > c->d_ops_cap) {
+            cudaFree(c->d_ops); c->d_ops = nullptr; c->d_ops_cap = 0;
+            CU(cudaMalloc(&c->d_ops, c->plan.ops.size() + 16));
+            c->d_ops_cap = c->plan.ops.size();
+        }
+        CU(cudaMemcpyAsync(c->d_ops, c->plan.ops.data(), c->plan.ops.size(), cudaMemcpyHostToDevice, c->stream));
+        c->plan_on_device = true;
+    }
+    if (c->p_slot != 0) return fail(ECM_B200_ESTATE, "stage 1 already run on this batch");
+    // Schedule: an item is (group of THREADS curves, chunk of the op stream).  Items are ordered
+    // chunk-major and a launch takes a run of consecutive items, at most one per SM; because a run
+    // is never longer than the number of groups, item (g, c-1) is always in an earlier launch.
+    const uint64_t nops = c->plan.ops.size();
+    uint32_t chunk = 32768;
+    if (c->groups > (uint32_t)c->num_sms) {
+        // several waves: finer chunks keep the last partial launch small
+        chunk = 8192;
+    }
+    c->chunk_len = chunk;
+    const uint64_t nchunks = (nops + chunk - 1) / chunk;
+    c->total_items = nchunks * c->groups;
+    c->next_item = 0;
+    const uint32_t per = std::min<uint32_t>(c->groups, (uint32_t)c->num_sms);
+    c->launches_total = (uint32_t)((c->total_items + per - 1) / per);
+    c->launches_issued = 0;
+    c->last_launches = 0;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    return ECM_B200_OK;
+}
+
+int ecm_b200_stage1_step(ecm_b200_ctx *c, uint32_t max_launches, int *done)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (c->total_items == 0) return fail(ECM_B200_ESTATE, "stage1_begin not called");
+    CU(cudaSetDevice(c->device));
+    const uint32_t per = std::min<uint32_t>(c->groups, (uint32_t)c->num_sms);
+    uint32_t n = 0;
+    while (c->next_item < c->total_items && n < max_launches) {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>(per, c->total_items - c->next_item);
+        c->eng->stage1(c->stream, blocks, c->d_state, c->cap, c->d_ops, c->plan.ops.size(), c->chunk_len, c->groups, c->next_item);
+        c->next_item += blocks; c->launches_issued++; c->last_launches++; n++;
+    }
+    CU(cudaGetLastError());
+    const bool fin = c->next_item >= c->total_items;
+    if (fin && !c->stage1_done) {
+        c->stage1_done = true;
+        c->p_slot = c->plan.final_slot;
+        CU(cudaEventRecord(c->ev1, c->stream));
+    }
+    if (done) *done = fin ? 1 : 0;
+    return ECM_B200_OK;
+}
+
+int ecm_b200_stage1_launches(const ecm_b200_ctx *c, uint32_t *total, uint32_t *issued)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (total) *total = c->launches_total;
+    if (issued) *issued = c->launches_issued;
+    return ECM_B200_OK;
+}
+
+int ecm_b200_sync(ecm_b200_ctx *c)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->stage1_done && c->last_launches) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms;
+    }
+    return ECM_B200_OK;
+}
+
+int ecm_b200_stage1(ecm_b200_ctx *c, uint64_t b1)
+{
+    int rc = ecm_b200_stage1_begin(c, b1); if (rc) return rc;
+    int done = 0;
+    rc = ecm_b200_stage1_step(c, 0xffffffffu, &done); if (rc) return rc;
+    return ecm_b200_sync(c);
+}
+
+int ecm_b200_last_timing(const ecm_b200_ctx *c, float *stage_ms, uint32_t *launches)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (stage_ms) *stage_ms = c->last_ms;
+    if (launches) *launches = c->last_launches;
+    return ECM_B200_OK;
+}
+
+int ecm_b200_read_stage1(ecm_b200_ctx *c, uint32_t *x, uint32_t *z, uint8_t *factor_flag, uint32_t *gcd_out)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (!c->have_curves) return fail(ECM_B200_ESTATE, "no curves loaded");
+    CU(cudaSetDevice(c->device));
+    const size_t words = (size_t)c->nl * c->count;
+    uint32_t *dx = c->d_io, *dz = c->d_io + words, *dg = c->d_io + 2 * words;
+    const bool want_flag = factor_flag || gcd_out;
+    c->eng->read_point(c->stream, c->d_state, c->cap, c->count, 2 * c->p_slot, 2 * c->p_slot + 1, x ? dx : nullptr, dz,
+                       want_flag ? c->d_flags : nullptr, gcd_out ? dg : nullptr);
+    CU(cudaGetLastError());
+    if (x) CU(cudaMemcpyAsync(x, dx, words * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (z) CU(cudaMemcpyAsync(z, dz, words * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (factor_flag) CU(cudaMemcpyAsync(factor_flag, c->d_flags, c->count, cudaMemcpyDeviceToHost, c->stream));
+    if (gcd_out) CU(cudaMemcpyAsync(gcd_out, dg, words * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return ECM_B200_OK;
+}
+
+int ecm_b200_stage2(ecm_b200_ctx *, uint64_t, uint64_t) { return fail(ECM_B200_ESTATE, "stage 2 not built yet"); }
+int ecm_b200_read_stage2(ecm_b200_ctx *, uint32_t *, uint8_t *, uint32_t *, uint8_t *) { return fail(ECM_B200_ESTATE, "stage 2 not built yet"); }
+
+int ecm_b200_fieldop(ecm_b200_ctx *c, int op, uint32_t count, const uint32_t *a, const uint32_t *b, uint32_t *r, int repeat)
+{
+    if (!c || !a || !b || !r || op < 0 || op > 3 || repeat < 1) return fail(ECM_B200_EINVAL, "bad argument");
+    if (count > c->cap) return fail(ECM_B200_EINVAL, "count exceeds the context's capacity");
+    CU(cudaSetDevice(c->device));
+    const size_t words = (size_t)c->nl * count;
+    CU(cudaMemcpyAsync(c->d_io, a, words * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_io + words, b, words * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    c->eng->fieldop(c->stream, op, count, c->d_io, c->d_io + words, c->d_io + 2 * words, repeat);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(r, c->d_io + 2 * words, words * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms; c->last_launches = 1;
+    return ECM_B200_OK;
+}
+
+// ---- planners --------------------------------------------------------------------------------
+uint64_t ecm_b200_plan_stage1(uint64_t b1, uint8_t *ops, uint64_t cap, uint64_t *counts)
+{
+    Stage1Plan p;
+    plan_stage1(b1, p);
+    if (ops && cap >= p.n_ops) memcpy(ops, p.ops.data(), p.n_ops);
+    if (counts) { counts[0] = p.ptadds; counts[1] = p.ptdups; }
+    return p.n_ops;
+}
+
+uint32_t ecm_b200_pair(uint64_t lo, uint64_t hi, uint32_t D, uint32_t U, uint32_t *pairmap_v, uint32_t *pairmap_u,
+                       uint32_t cap, uint32_t *amin_final, uint32_t *npairs)
+{
+    Stage2Params p; p.D = D; p.U = U; p.L = 2 * U; p.R = 0;
+    std::vector<uint32_t> v, u;
+    uint32_t steps = pair_plan(lo, hi, p, v, u, amin_final, npairs);
+    if (pairmap_v && pairmap_u && cap >= steps) { memcpy(pairmap_v, v.data(), steps * 4ull); memcpy(pairmap_u, u.data(), steps * 4ull); }
+    return steps;
+}
+
+void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R)
+{
+    Stage2Params p = stage2_params(b1);
+    if (D) *D = p.D; if (U) *U = p.U; if (L) *L = p.L; if (R) *R = p.R;
+}
+
+int ecm_b200_measure_imad_peak(int, double *, double *) { return fail(ECM_B200_ESTATE, "not built yet"); }
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// engine.hpp -- host-side interface to the kernels of one compiled limb count.  Each limb count
+// is its own translation unit (engine_inst.cu, -DECM_NL=n) so that they compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+namespace ecmb200 {
+
+typedef std::vector<uint32_t> Big;
+
+struct Engine {
+    int nl = 0, threads_s1 = 0, smem_s1 = 0;
+    size_t params_bytes = 0;
+    virtual ~Engine() {}
+    virtual void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, uint32_t m0inv) = 0;
+    virtual const void *params_host() const = 0;        // ModParams<NL> image to copy to the device
+    virtual void set_params_device(const void *d) = 0;  // device copy for the out-of-line kernels
+    virtual cudaError_t prepare() = 0;
+    virtual void stage1(cudaStream_t st, uint32_t blocks, uint32_t *state, uint32_t cap, const uint8_t *ops, uint64_t nops,
+                        uint32_t chunk_len, uint32_t groups, uint64_t item0) = 0;
+    virtual void load_curves(cudaStream_t st, uint32_t *state, uint32_t cap, uint32_t count, const uint32_t *x, const uint32_t *s) = 0;
+    virtual void build_curves(cudaStream_t st, uint32_t *state, uint32_t cap, uint32_t count, const uint32_t *uv, uint8_t *ok) = 0;
+    virtual void read_point(cudaStream_t st, const uint32_t *state, uint32_t cap, uint32_t count, uint32_t xs, uint32_t zs,
+                            uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g) = 0;
+    virtual void fieldop(cudaStream_t st, int op, uint32_t count, const uint32_t *a, const uint32_t *b, uint32_t *r, int repeat) = 0;
+};
+
+extern void count_launch();
+
+}  // namespace ecmb200

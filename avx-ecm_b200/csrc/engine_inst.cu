@@ -1,0 +1,64 @@
+// engine_inst.cu -- instantiates every kernel for ONE limb count (compile with -DECM_NL=<n>).
+#include "engine.hpp"
+#include "kernels.cuh"
+
+#ifndef ECM_NL
+#error "compile with -DECM_NL=<limbs>"
+#endif
+
+namespace ecmb200 {
+
+template <int NL>
+struct EngineT : Engine {
+    ModParams<NL> P;
+    const ModParams<NL> *Pg = nullptr;
+    EngineT()
+    {
+        nl = NL; threads_s1 = BlockCfg<NL, NSLOT_S1>::THREADS; smem_s1 = BlockCfg<NL, NSLOT_S1>::smem;
+        params_bytes = sizeof(ModParams<NL>);
+    }
+    void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, uint32_t m0inv) override
+    {
+        for (int k = 0; k < NL; k++) { P.n[k] = n[k]; P.one[k] = one[k]; P.r2[k] = r2[k]; P.r3[k] = r3[k]; P.rrefinv[k] = rri[k]; }
+        P.m0inv = m0inv;
+    }
+    const void *params_host() const override { return &P; }
+    void set_params_device(const void *d) override { Pg = static_cast<const ModParams<NL> *>(d); }
+    cudaError_t prepare() override
+    {
+        return cudaFuncSetAttribute(k_stage1<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s1);
+    }
+    void stage1(cudaStream_t st, uint32_t blocks, uint32_t *state, uint32_t cap, const uint8_t *ops, uint64_t nops,
+                uint32_t chunk_len, uint32_t groups, uint64_t item0) override
+    {
+        k_stage1<NL><<<blocks, threads_s1, smem_s1, st>>>(P, state, cap, ops, nops, chunk_len, groups, item0);
+        count_launch();
+    }
+    void load_curves(cudaStream_t st, uint32_t *state, uint32_t cap, uint32_t count, const uint32_t *x, const uint32_t *s) override
+    {
+        k_load_curves<NL><<<(cap + 127) / 128, 128, 0, st>>>(Pg, state, cap, count, x, s);
+        count_launch();
+    }
+    void build_curves(cudaStream_t st, uint32_t *state, uint32_t cap, uint32_t count, const uint32_t *uv, uint8_t *ok) override
+    {
+        k_build_curves<NL><<<(cap + 63) / 64, 64, 0, st>>>(Pg, state, cap, count, uv, ok);
+        count_launch();
+    }
+    void read_point(cudaStream_t st, const uint32_t *state, uint32_t cap, uint32_t count, uint32_t xs, uint32_t zs,
+                    uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g) override
+    {
+        k_read_point<NL><<<(count + 63) / 64, 64, 0, st>>>(Pg, state, cap, count, xs, zs, x, z, flag, g);
+        count_launch();
+    }
+    void fieldop(cudaStream_t st, int op, uint32_t count, const uint32_t *a, const uint32_t *b, uint32_t *r, int repeat) override
+    {
+        k_fieldop<NL><<<(count + 127) / 128, 128, 0, st>>>(P, Pg, op, count, a, b, r, repeat);
+        count_launch();
+    }
+};
+
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+Engine *CAT(make_engine_, ECM_NL)() { return new EngineT<ECM_NL>(); }
+
+}  // namespace ecmb200

@@ -1,0 +1,232 @@
+// kernels.cuh -- __global__ entry points, templated on the limb count NL.
+// Device state of a batch: state[(slot*NL + limb) * cap + curve]  (limb-major, curve fastest:
+// a warp's 32 curves read 128 contiguous bytes per limb -- the coalesced analogue of the
+// reference's bignum.data[lane + word*VECLEN], vec_common.c:32-54).
+#pragma once
+#include "vm.cuh"
+#include "modinv.cuh"
+
+namespace ecmb200 {
+
+constexpr int kSmemBudget = 227 * 1024;
+template <int NL, int NSLOT>
+struct BlockCfg {
+    static constexpr int per_thread = NSLOT * NL * 4;
+    static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
+    static constexpr int THREADS = fit > 512 ? 512 : (fit < 32 ? 32 : fit);
+    static constexpr int smem = per_thread * THREADS;
+};
+
+template <int NL>
+__device__ __forceinline__ void gload(uint32_t (&r)[NL], const uint32_t *state, uint32_t cap, uint32_t slot, uint32_t curve)
+{
+#pragma unroll
+    for (int k = 0; k < NL; k++) r[k] = state[((size_t)slot * NL + k) * cap + curve];
+}
+template <int NL>
+__device__ __forceinline__ void gstore(uint32_t *state, uint32_t cap, uint32_t slot, uint32_t curve, const uint32_t (&r)[NL])
+{
+#pragma unroll
+    for (int k = 0; k < NL; k++) state[((size_t)slot * NL + k) * cap + curve] = r[k];
+}
+
+// ---- stage 1: interpret macro-ops [chunk*chunk_len, ...) for one group of THREADS curves ------
+template <int NL>
+__global__ void __launch_bounds__(BlockCfg<NL, NSLOT_S1>::THREADS, 1)
+k_stage1(const ModParams<NL> P, uint32_t *__restrict__ state, uint32_t cap, const uint8_t *__restrict__ ops,
+         uint64_t nops, uint32_t chunk_len, uint32_t groups, uint64_t item0)
+{
+    constexpr int THREADS = BlockCfg<NL, NSLOT_S1>::THREADS;
+    extern __shared__ uint32_t smem[];
+    const uint64_t item = item0 + blockIdx.x;
+    const uint32_t g = (uint32_t)(item % groups);
+    const uint64_t chunk = item / groups;
+    const uint32_t curve = g * THREADS + threadIdx.x;
+    Slots<NL, THREADS> S{smem + threadIdx.x};
+
+    uint32_t r[NL];
+#pragma unroll 1
+    for (uint32_t s = 0; s < NSLOT_S1; s++) { gload<NL>(r, state, cap, s, curve); S.store(s, r); }
+
+    uint64_t i = chunk * chunk_len;
+    const uint64_t end = (i + chunk_len < nops) ? i + chunk_len : nops;
+    const uint32_t *ops32 = reinterpret_cast<const uint32_t *>(ops);
+    uint32_t cur = 0;
+#pragma unroll 1
+    for (; i < end; i++) {
+        if ((i & 3) == 0) cur = __ldg(ops32 + (i >> 2));
+        const uint32_t byte = cur & 0xffu;
+        cur >>= 8;
+        const uint32_t type = byte & 7u;
+        const uint32_t permbits = c_perm[byte >> 3];
+#pragma unroll 1
+        for (int k = 0;; k++) {
+            const uint32_t u = c_prog_s1[type][k];
+            if ((u & 15u) == U_END) break;
+            exec_uop<NL, THREADS>(S, u, permbits, P);
+        }
+    }
+#pragma unroll 1
+    for (uint32_t s = 0; s < NSLOT_S1; s++) { S.load(r, s); gstore<NL>(state, cap, s, curve, r); }
+}
+
+// ---- out-of-line helpers for the set-up / read-out kernels (speed is irrelevant there; keeping
+// one copy of each routine keeps compile time and code size down).  Pg points to a copy of the
+// parameters in global memory.
+template <int NL>
+__device__ __noinline__ void nm_mul(uint32_t *r, const uint32_t *a, const uint32_t *b, const ModParams<NL> *Pg)
+{
+    uint32_t x[NL], y[NL], z[NL];
+#pragma unroll
+    for (int k = 0; k < NL; k++) { x[k] = a[k]; y[k] = b[k]; }
+    mont_mul<NL>(z, x, y, *Pg);
+#pragma unroll
+    for (int k = 0; k < NL; k++) r[k] = z[k];
+}
+template <int NL>
+__device__ __noinline__ void nm_addsub(uint32_t *r, const uint32_t *a, const uint32_t *b, bool sub, const ModParams<NL> *Pg)
+{
+    uint32_t x[NL], y[NL], z[NL];
+#pragma unroll
+    for (int k = 0; k < NL; k++) { x[k] = a[k]; y[k] = b[k]; }
+    if (sub) mod_sub<NL>(z, x, y, *Pg); else mod_add<NL>(z, x, y, *Pg);
+#pragma unroll
+    for (int k = 0; k < NL; k++) r[k] = z[k];
+}
+template <int NL>
+__device__ __noinline__ bool nm_inverse(uint32_t *inv, uint32_t *g, const uint32_t *x, const ModParams<NL> *Pg)
+{
+    uint32_t a[NL], i[NL], gg[NL];
+#pragma unroll
+    for (int k = 0; k < NL; k++) a[k] = x[k];
+    const bool ok = mod_inverse<NL, true>(i, gg, a, *Pg);
+#pragma unroll
+    for (int k = 0; k < NL; k++) { inv[k] = i[k]; g[k] = gg[k]; }
+    return ok;
+}
+
+// ---- curve set-up -----------------------------------------------------------------------------
+// host-built curves: plain x = X/Z and s = (A+2)/4  ->  Montgomery form, Z = 1; P sits in point slot 0
+template <int NL>
+__global__ void k_load_curves(const ModParams<NL> *Pg, uint32_t *state, uint32_t cap, uint32_t count,
+                              const uint32_t *x, const uint32_t *s)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cap) return;
+    const uint32_t src = c < count ? c : count - 1;          // padding lanes replicate the last curve
+    uint32_t a[NL], t[NL];
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+        const uint32_t *in = which ? s : x;
+        for (int k = 0; k < NL; k++) a[k] = in[(size_t)k * count + src];
+        nm_mul<NL>(t, a, Pg->r2, Pg);
+        for (int k = 0; k < NL; k++) state[((size_t)(which ? SP : 0) * NL + k) * cap + c] = t[k];
+    }
+    for (int k = 0; k < NL; k++) state[((size_t)1 * NL + k) * cap + c] = Pg->one[k];
+}
+
+// Suyama "param 0" curve from u = sigma^2-5, v = 4*sigma (both already reduced mod N, 4 limbs each,
+// [limb][curve]); build_one_curve, ecm.c:1587-1772:
+//   X = u^3 / v^3,  Z = 1,  s = (v-u)^3 (3u+v) / (16 u^3 v)
+// One shared inversion of (v^3 * 16u^3v) replaces the reference's two mpz_invert calls; the
+// quotients are the same residues.  ok[c] = 0 when that product is not invertible mod N.
+template <int NL>
+__global__ void k_build_curves(const ModParams<NL> *Pg, uint32_t *state, uint32_t cap, uint32_t count,
+                               const uint32_t *uv, uint8_t *ok)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cap) return;
+    const uint32_t src = c < count ? c : count - 1;
+    uint32_t u[NL], v[NL], t1[NL], t2[NL], u3[NL], v3[NL], num[NL], den[NL], inv[NL], g[NL];
+    for (int k = 0; k < NL; k++) {
+        u[k] = (k < 4) ? uv[(size_t)k * count + src] : 0;
+        v[k] = (k < 4) ? uv[(size_t)(4 + k) * count + src] : 0;
+    }
+    nm_mul<NL>(u, u, Pg->r2, Pg);                    // Montgomery form
+    nm_mul<NL>(v, v, Pg->r2, Pg);
+    nm_mul<NL>(t1, u, u, Pg); nm_mul<NL>(u3, t1, u, Pg);          // u^3
+    nm_mul<NL>(t1, v, v, Pg); nm_mul<NL>(v3, t1, v, Pg);          // v^3
+    nm_addsub<NL>(t1, v, u, true, Pg);                            // v-u
+    nm_mul<NL>(t2, t1, t1, Pg); nm_mul<NL>(num, t2, t1, Pg);      // (v-u)^3
+    nm_addsub<NL>(t1, u, u, false, Pg); nm_addsub<NL>(t1, t1, u, false, Pg); nm_addsub<NL>(t1, t1, v, false, Pg);   // 3u+v
+    nm_mul<NL>(num, num, t1, Pg);                                 // (v-u)^3 (3u+v)
+    nm_mul<NL>(den, u3, v, Pg);                                   // u^3 v
+    for (int k = 0; k < 4; k++) nm_addsub<NL>(den, den, den, false, Pg);   // 16 u^3 v
+    nm_mul<NL>(t1, den, v3, Pg);                                  // den * v^3   (Montgomery form)
+    const bool good = nm_inverse<NL>(inv, g, t1, Pg);             // (den v^3 R)^-1
+    nm_mul<NL>(inv, inv, Pg->r3, Pg);                             // -> (den v^3)^-1 in Montgomery form
+    nm_mul<NL>(t1, inv, den, Pg);                                 // 1/v^3
+    nm_mul<NL>(t2, inv, v3, Pg);                                  // 1/den
+    nm_mul<NL>(t1, t1, u3, Pg);                                   // X = u^3/v^3
+    nm_mul<NL>(t2, t2, num, Pg);                                  // s
+    for (int k = 0; k < NL; k++) {
+        state[((size_t)0 * NL + k) * cap + c] = t1[k];
+        state[((size_t)1 * NL + k) * cap + c] = Pg->one[k];
+        state[((size_t)SP * NL + k) * cap + c] = t2[k];
+    }
+    if (c < count) ok[c] = good ? 1 : 0;
+}
+
+// ---- results ---------------------------------------------------------------------------------
+// X*1, Z*1 leave Montgomery form (ecm.c:1327-1331); gcd(Z,N) is the stage-1 factor test
+// (ecm.c:1335-1342, check_factor ecm.c:2542-2557: 1 < g < N).
+template <int NL>
+__global__ void k_read_point(const ModParams<NL> *Pg, const uint32_t *state, uint32_t cap, uint32_t count,
+                             uint32_t xslot, uint32_t zslot, uint32_t *x_out, uint32_t *z_out,
+                             uint8_t *flag, uint32_t *g_out)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= count) return;
+    uint32_t a[NL], one[NL], r[NL], g[NL], dummy[NL];
+    for (int k = 0; k < NL; k++) one[k] = (k == 0);
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+        uint32_t *out = which ? z_out : x_out;
+        if (!out && !(which && flag)) continue;
+        for (int k = 0; k < NL; k++) a[k] = state[((size_t)(which ? zslot : xslot) * NL + k) * cap + c];
+        if (out) {
+            nm_mul<NL>(r, a, one, Pg);
+            for (int k = 0; k < NL; k++) out[(size_t)k * count + c] = r[k];
+        }
+    }
+    if (flag) {                                   // a = Z (Montgomery form; gcd(Z*R,N) = gcd(Z,N))
+        nm_inverse<NL>(dummy, g, a, Pg);
+        bool is_one = (g[0] == 1), is_n = true;
+        for (int k = 0; k < NL; k++) { if (k && g[k]) is_one = false; if (g[k] != Pg->n[k]) is_n = false; }
+        const bool found = !is_one && !is_n;
+        flag[c] = found ? 1 : 0;
+        if (g_out) for (int k = 0; k < NL; k++) g_out[(size_t)k * count + c] = found ? g[k] : 0;
+    }
+}
+
+// ---- field-op hook ----------------------------------------------------------------------------
+// op 0 mul, 1 sqr, 2 add, 3 sub; `repeat` chained applications (a <- op(a,b)) so that the same
+// kernel serves as the modmul throughput micro-benchmark.
+template <int NL>
+__global__ void k_fieldop(const ModParams<NL> P, const ModParams<NL> *Pg, int op, uint32_t count, const uint32_t *a_in,
+                          const uint32_t *b_in, uint32_t *r_out, int repeat)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= count) return;
+    uint32_t a[NL], b[NL], r[NL], one[NL];
+    for (int k = 0; k < NL; k++) { a[k] = a_in[(size_t)k * count + c]; b[k] = b_in[(size_t)k * count + c]; one[k] = (k == 0); }
+    nm_mul<NL>(a, a, Pg->r2, Pg);
+    nm_mul<NL>(b, b, Pg->r2, Pg);
+#pragma unroll 1
+    for (int it = 0; it < repeat; it++) {
+        if (op <= 1) {
+            if (op == 1) {
+#pragma unroll
+                for (int k = 0; k < NL; k++) b[k] = a[k];
+            }
+            mont_mul<NL>(r, a, b, P);
+        } else if (op == 2) mod_add<NL>(r, a, b, P);
+        else mod_sub<NL>(r, a, b, P);
+#pragma unroll
+        for (int k = 0; k < NL; k++) a[k] = r[k];
+    }
+    nm_mul<NL>(r, a, one, Pg);
+    for (int k = 0; k < NL; k++) r_out[(size_t)k * count + c] = r[k];
+}
+
+}  // namespace ecmb200

@@ -1,0 +1,131 @@
+// vm.cuh -- the curve-arithmetic "field-op machine".
+//
+// One thread owns one curve.  All curves of a batch execute the same op stream (the PRAC
+// chain for a prime does not depend on the curve), so the host compiles stage 1 / stage 2 into
+// a compact stream of macro-ops once and every thread of the grid interprets it with zero
+// divergence.  A macro-op expands (from a table in constant memory) into field micro-ops on
+// numbered slots; slots live in shared memory as [slot][limb][thread] (bank = thread, conflict
+// free), operands are pulled into registers for the multiply.  Only ONE copy of the unrolled
+// Montgomery multiply exists in the kernel, which keeps the instruction footprint small.
+//
+// Reference semantics reproduced (Appendix A of SURVEY.md):
+//   vec_add        ecm.c:407-443      vec_duplicate  ecm.c:445-457
+//   prac() body    ecm.c:603-873      ecm_stage1     ecm.c:1806-1854
+// Pointer swaps of the reference (ecm.c:624-629, 704-711) cost nothing here: the host tracks
+// which physical point slot currently plays A, B, C, T and encodes that permutation in the
+// macro-op byte.
+#pragma once
+#include "mp.cuh"
+
+namespace ecmb200 {
+
+// ---- micro-ops --------------------------------------------------------------------------
+enum : uint32_t { U_MUL = 0, U_SQR = 1, U_ADD = 2, U_SUB = 3, U_ADDSUB = 4, U_COPY = 5, U_END = 15 };
+// symbolic operands: 0..7 point coordinates resolved through the permutation, 8.. fixed slots
+enum : uint32_t { AX = 0, AZ, BX, BZ, CX, CZ, TX, TZ, S1 = 8, D1, S2, D2, SP, NSLOT_S1 };
+#define UOP(op, d, d2, x, y) ((uint32_t)(op) | ((uint32_t)(d) << 4) | ((uint32_t)(d2) << 8) | ((uint32_t)(x) << 12) | ((uint32_t)(y) << 16))
+
+// vec_add(Pin -> Pout) with the current s1,d1,s2,d2; temporaries reuse d1 / s1 (dead after
+// their first use):  d1 = d1*s2 ; s1 = s1*d2 ; (d1,s1) = (d1+s1, d1-s1) ; d1 = d1^2 ; s1 = s1^2 ;
+// Pout.X = d1*Pin.Z ; Pout.Z = s1*Pin.X                                   (ecm.c:417-439)
+#define PROG_ADD(PinX, PinZ, PoutX, PoutZ)                                                     \
+    UOP(U_MUL, D1, 0, D1, S2), UOP(U_MUL, S1, 0, S1, D2), UOP(U_ADDSUB, D1, S1, D1, S1),         \
+    UOP(U_SQR, D1, 0, D1, D1), UOP(U_SQR, S1, 0, S1, S1), UOP(U_MUL, PoutX, 0, D1, PinZ),        \
+    UOP(U_MUL, PoutZ, 0, S1, PinX)
+// vec_duplicate(s,d -> P), scratch = a dead sum slot:  d = d^2 ; s = s^2 ; P.X = d*s ;
+// tmp = s-d ; s = tmp*sp ; s = s+d ; P.Z = s*tmp                           (ecm.c:447-454)
+#define PROG_DUP(s, d, tmp, PX, PZ)                                                            \
+    UOP(U_SQR, d, 0, d, d), UOP(U_SQR, s, 0, s, s), UOP(U_MUL, PX, 0, d, s), UOP(U_SUB, tmp, 0, s, d), \
+    UOP(U_MUL, s, 0, tmp, SP), UOP(U_ADD, s, 0, s, d), UOP(U_MUL, PZ, 0, s, tmp)
+#define PROG_SUMS(PX, PZ, s, d) UOP(U_ADDSUB, s, d, PX, PZ)
+
+// ---- stage-1 macro-ops (low 3 bits of the stream byte; high 5 bits = permutation index) ----
+enum : uint32_t { M_DBL = 0, M_INIT = 1, M_C3 = 2, M_C4 = 3, M_C5 = 4, M_C9 = 5, M_FINAL = 6, M_NOP = 7 };
+#define MAXPROG 20
+static __constant__ uint32_t c_prog_s1[8][MAXPROG] = {
+    // M_DBL: P (held in logical T) doubled in place                      (ecm.c:1816-1822)
+    { PROG_SUMS(TX, TZ, S1, D1), PROG_DUP(S1, D1, S2, TX, TZ), UOP(U_END, 0, 0, 0, 0) },
+    // M_INIT: P is in logical B (the host renamed it); C = P ; A = 2P      (ecm.c:603-613)
+    { UOP(U_COPY, CX, 0, BX, 0), UOP(U_COPY, CZ, 0, BZ, 0), PROG_SUMS(BX, BZ, S1, D1),
+      PROG_DUP(S1, D1, S2, AX, AZ), UOP(U_END, 0, 0, 0, 0) },
+    // M_C3: T = B + A (C) ; host then rotates (B,T,C)                     (ecm.c:683-713)
+    { PROG_SUMS(BX, BZ, S1, D1), PROG_SUMS(AX, AZ, S2, D2), PROG_ADD(CX, CZ, TX, TZ), UOP(U_END, 0, 0, 0, 0) },
+    // M_C4: B = B + A (C) ; A = 2A                                        (ecm.c:714-726)
+    { PROG_SUMS(BX, BZ, S1, D1), PROG_SUMS(AX, AZ, S2, D2), PROG_ADD(CX, CZ, BX, BZ),
+      PROG_DUP(S2, D2, S1, AX, AZ), UOP(U_END, 0, 0, 0, 0) },
+    // M_C5: C = C + A (B) ; A = 2A                                        (ecm.c:728-740)
+    { PROG_SUMS(CX, CZ, S1, D1), PROG_SUMS(AX, AZ, S2, D2), PROG_ADD(BX, BZ, CX, CZ),
+      PROG_DUP(S2, D2, S1, AX, AZ), UOP(U_END, 0, 0, 0, 0) },
+    // M_C9: C = C + B (A) ; B = 2B                                        (ecm.c:853-865)
+    { PROG_SUMS(CX, CZ, S1, D1), PROG_SUMS(BX, BZ, S2, D2), PROG_ADD(AX, AZ, CX, CZ),
+      PROG_DUP(S2, D2, S1, BX, BZ), UOP(U_END, 0, 0, 0, 0) },
+    // M_FINAL: P = A + B (C), written to logical T                        (ecm.c:868-873)
+    { PROG_SUMS(AX, AZ, S1, D1), PROG_SUMS(BX, BZ, S2, D2), PROG_ADD(CX, CZ, TX, TZ), UOP(U_END, 0, 0, 0, 0) },
+    { UOP(U_END, 0, 0, 0, 0) },
+};
+
+// permutation index -> physical point slot of (A,B,C,T), 2 bits each (A lowest)
+static __constant__ uint8_t c_perm[24] = {
+    0xE4, 0xB4, 0xD8, 0x78, 0x9C, 0x6C, 0xE1, 0xB1, 0xC9, 0x39, 0x8D, 0x2D,
+    0xD2, 0x72, 0xC6, 0x36, 0x4E, 0x1E, 0x93, 0x63, 0x87, 0x27, 0x4B, 0x1B };
+
+// ---- slot access: [slot][limb][thread] in shared memory ------------------------------------
+template <int NL, int THREADS>
+struct Slots {
+    uint32_t *base;   // smem + threadIdx.x
+    __device__ __forceinline__ void load(uint32_t (&r)[NL], uint32_t slot) const
+    {
+        const uint32_t *p = base + slot * (NL * THREADS);
+#pragma unroll
+        for (int k = 0; k < NL; k++) r[k] = p[k * THREADS];
+    }
+    __device__ __forceinline__ void store(uint32_t slot, const uint32_t (&r)[NL]) const
+    {
+        uint32_t *p = base + slot * (NL * THREADS);
+#pragma unroll
+        for (int k = 0; k < NL; k++) p[k * THREADS] = r[k];
+    }
+};
+
+__device__ __forceinline__ uint32_t resolve(uint32_t sym, uint32_t permbits)
+{
+    return (sym < 8) ? (2u * ((permbits >> (2u * (sym >> 1))) & 3u) + (sym & 1u)) : sym;
+}
+
+// Execute one micro-op on the slot file.
+template <int NL, int THREADS>
+__device__ __forceinline__ void exec_uop(const Slots<NL, THREADS> &S, uint32_t u, uint32_t permbits,
+                                         const ModParams<NL> &P)
+{
+    const uint32_t op = u & 15u;
+    const uint32_t d = resolve((u >> 4) & 15u, permbits);
+    const uint32_t x = resolve((u >> 12) & 15u, permbits);
+    const uint32_t y = resolve((u >> 16) & 15u, permbits);
+    uint32_t a[NL], b[NL], r[NL];
+    S.load(a, x);
+    if (op == U_MUL || op == U_SQR) {
+        // one shared multiply body serves both (dedicated squaring: see DESIGN.md roadmap)
+        S.load(b, y);
+        mont_mul<NL>(r, a, b, P);
+        S.store(d, r);
+    } else if (op == U_ADDSUB) {
+        const uint32_t d2 = resolve((u >> 8) & 15u, permbits);
+        S.load(b, y);
+        mod_add<NL>(r, a, b, P);
+        S.store(d, r);
+        mod_sub<NL>(r, a, b, P);
+        S.store(d2, r);
+    } else if (op == U_ADD) {
+        S.load(b, y);
+        mod_add<NL>(r, a, b, P);
+        S.store(d, r);
+    } else if (op == U_SUB) {
+        S.load(b, y);
+        mod_sub<NL>(r, a, b, P);
+        S.store(d, r);
+    } else {  // U_COPY
+        S.store(d, a);
+    }
+}
+
+}  // namespace ecmb200

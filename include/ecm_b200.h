@@ -1,0 +1,109 @@
+/*
+ * ecm_b200.h -- C ABI of the B200 ECM engine (libecm_b200.so).
+ *
+ * This is the drop-in boundary for avx-ecm's hot path.  The reference reaches its vector
+ * arithmetic through four thread-pool work functions, one call per phase per batch
+ * (ecm.c:1130-1133, 167-246): build curves, stage 1, stage-2 init, stage-2 pair.  A GPU cannot
+ * be fed per field op (avx_ecm.h:205-209), so the boundary sits at that work-function level:
+ * each entry point below replaces one of those phases for a whole batch of curves that all
+ * share N.  Plain pointers and sizes only; all big numbers are little-endian arrays of
+ * 32-bit limbs.  Batch buffers are limb-major with the curve index fastest,
+ *        buf[limb * count + curve]
+ * i.e. the layout of the reference's bignum.data[lane + word*VECLEN] (main.c:63-89,117-138).
+ *
+ * Return value: 0 on success, negative on error (ecm_b200_last_error() has the text).
+ * There is no CPU fallback: every call fails with ECM_B200_ENODEV when no CUDA device is
+ * usable.
+ */
+#ifndef ECM_B200_H
+#define ECM_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECM_B200_OK 0
+#define ECM_B200_EINVAL -1
+#define ECM_B200_ENODEV -2
+#define ECM_B200_ECUDA -3
+#define ECM_B200_ESTATE -4
+#define ECM_B200_ENOMEM -5
+
+typedef struct ecm_b200_ctx ecm_b200_ctx;
+
+/* ---- context (replaces thread_init/monty_alloc, main.c:597-640, 834-970) -------------------
+ * n: modulus, nlimbs 32-bit limbs, little endian, must be odd and > 1.  max_curves: capacity of
+ * the batch.  The Montgomery constants (R = 2^(32*k), one = R mod N, -N^-1 mod 2^32) are derived
+ * here; residues never depend on R.                                         */
+int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimbs, uint32_t max_curves);
+void ecm_b200_destroy(ecm_b200_ctx *ctx);
+const char *ecm_b200_last_error(void);
+/* number of 32-bit limbs the engine computes with (>= nlimbs of N; kernels exist for a fixed set) */
+int ecm_b200_limbs(const ecm_b200_ctx *ctx);
+
+/* ---- phase 0: curve construction (replaces build_one_curve, ecm.c:1548-1803, and
+ * ecm_build_curve_work_fcn, ecm.c:201-246).  GMP-ECM "param 0" Suyama curves, curve i uses
+ * sigma[i].  Computed on the device (one modular inversion per curve).                        */
+int ecm_b200_build_curves(ecm_b200_ctx *ctx, uint32_t count, const uint64_t *sigma);
+/* Same phase with host-built curves: plain residues X = x/z, s = (A+2)/4, Z is set to 1
+ * (what insert_mpz_to_vec receives in ecm.c:222-228, minus the Montgomery shift).             */
+int ecm_b200_load_curves(ecm_b200_ctx *ctx, uint32_t count, const uint32_t *x, const uint32_t *s);
+
+/* ---- phase 1: stage 1 (replaces ecm_stage1, ecm.c:1806-1854) --------------------------------
+ * Multiplies every curve's point by 2^e * prod p^k for p^k < B1.  The PRAC chains are planned on
+ * the host (ecm_b200_plan_stage1) and cached in the context.                                   */
+int ecm_b200_stage1(ecm_b200_ctx *ctx, uint64_t b1);
+/* Asynchronous form: enqueue at most max_launches kernel launches of the stage-1 schedule and
+ * return; *done is set to 1 when the whole stage has been enqueued.  Used for time slicing.   */
+int ecm_b200_stage1_begin(ecm_b200_ctx *ctx, uint64_t b1);
+int ecm_b200_stage1_step(ecm_b200_ctx *ctx, uint32_t max_launches, int *done);
+int ecm_b200_stage1_launches(const ecm_b200_ctx *ctx, uint32_t *total, uint32_t *issued);
+int ecm_b200_sync(ecm_b200_ctx *ctx);
+
+/* Results of stage 1 as the reference writes them to save_b1.txt (ecm.c:1327-1380): X and Z out
+ * of Montgomery form, limb-major [limb*count+curve] with ecm_b200_limbs() limbs; factor_flag[i]
+ * is 1 when gcd(Z,N) is a proper factor (check_factor, ecm.c:2542-2557) and then gcd_out holds it
+ * (same layout).  Any output pointer may be NULL.                                              */
+int ecm_b200_read_stage1(ecm_b200_ctx *ctx, uint32_t *x, uint32_t *z, uint8_t *factor_flag, uint32_t *gcd_out);
+
+/* ---- phases 2+3: stage 2 (replaces ecm_stage2_init ecm.c:2201-2340 and ecm_stage2_pair
+ * ecm.c:2342-2540 driven by pair() ecm.c:2559-2910).  Runs the pairing continuation over all
+ * primes in [b1, b2) in the reference's 1e8 ranges, D and U as the reference selects them.     */
+int ecm_b200_stage2(ecm_b200_ctx *ctx, uint64_t b1, uint64_t b2);
+/* acc: stage-2 accumulator out of Montgomery form; factor_flag/gcd_out as above for gcd(acc,N)
+ * (ecm.c:1485-1497); inv_fail[i] = 1 when curve i met a non-invertible element.                */
+int ecm_b200_read_stage2(ecm_b200_ctx *ctx, uint32_t *acc, uint8_t *factor_flag, uint32_t *gcd_out, uint8_t *inv_fail);
+
+/* ---- host-side planners (the scalar control flow the reference also runs on the host) ------
+ * Stage-1 op stream for B1 (prac(), lucas_cost(), ecm.c:479-884, driven as in ecm.c:1815-1832).
+ * Returns the number of stream bytes (also when ops==NULL or cap too small).  counts[0..1] =
+ * point additions / doublings, the numbers the reference prints (ecm.c:1849).                  */
+uint64_t ecm_b200_plan_stage1(uint64_t b1, uint8_t *ops, uint64_t cap, uint64_t *counts);
+/* Montgomery's PAIR for the primes of [lo,hi) (pair(), ecm.c:2559-2910): fills pairmap_v/u,
+ * returns the number of steps (also when the arrays are NULL / cap too small).                */
+uint32_t ecm_b200_pair(uint64_t lo, uint64_t hi, uint32_t D, uint32_t U, uint32_t *pairmap_v,
+                       uint32_t *pairmap_u, uint32_t cap, uint32_t *amin_final, uint32_t *npairs);
+/* Stage-2 geometry chosen for B1 (thread_init, main.c:834-970): D, U, L, R.                    */
+void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R);
+
+/* ---- field-op hook (the reference's operator table vecmulmod_ptr ... avx_ecm.h:205-209) -----
+ * op: 0 mul, 1 sqr, 2 add, 3 sub on count independent operand pairs, plain residues in/out
+ * (the engine enters and leaves Montgomery form around the op).  For tests and micro-benchmarks. */
+int ecm_b200_fieldop(ecm_b200_ctx *ctx, int op, uint32_t count, const uint32_t *a, const uint32_t *b, uint32_t *r, int repeat);
+
+/* ---- instrumentation -------------------------------------------------------------------------
+ * Kernel launches issued by this library in this process, and device time (ms) spent in them
+ * as measured with CUDA events on the context's stream by the last stage call.                 */
+uint64_t ecm_b200_launch_count(void);
+int ecm_b200_last_timing(const ecm_b200_ctx *ctx, float *stage_ms, uint32_t *launches);
+/* Live integer-multiply peak of this GPU: 32x32->64 products per second retired by dependent-free
+ * IMAD.WIDE.U32 chains (the instruction the multiply is built from).                           */
+int ecm_b200_measure_imad_peak(int device, double *products_per_sec, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

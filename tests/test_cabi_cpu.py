@@ -1,0 +1,85 @@
+"""CPU-side checks of the product's host logic: the C-ABI library loads and exports every symbol
+declared in include/ecm_b200.h, and the host planners (PRAC op stream, PAIR, stage-2 geometry)
+agree with the oracle / the reference's printed counters.  No GPU compute is called."""
+import ctypes, os, re
+import pytest
+from conftest import GOLDEN, ROOT
+import oracle_lib as O
+import avx_ecm_b200 as E
+
+TYPE_CH = {0: "D", 1: "I", 2: "3", 3: "4", 4: "5", 5: "9", 6: "F"}
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ecm_b200.h")).read()
+    declared = set(re.findall(r"\b(ecm_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(E.EXPORTS)
+    L = ctypes.CDLL(E.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(E.EcmError, match="no usable CUDA device"):
+        E.EcmContext((1 << 127) - 1, 8)
+
+
+@pytest.mark.parametrize("b1", [50, 400, 3000, 20000, 100000])
+def test_stage1_plan_matches_oracle_trace(b1):
+    ops, adds, dups = E.plan_stage1(b1)
+    mine = "".join(TYPE_CH[b & 7] for b in ops)
+    ref = O.stage1_trace(b1).decode().replace("S", "")
+    assert mine == ref
+    assert adds == sum(ref.count(c) for c in "3459F")
+    assert dups == sum(ref.count(c) for c in "DI459")
+
+
+def test_stage1_plan_counts_match_reference_printout():
+    # ecm.c:1849 prints these for B1=1e6; golden files hold them too
+    _, adds, dups = E.plan_stage1(1000000)
+    assert (adds, dups) == (1980817, 217929)
+    g = GOLDEN["csh250k_stage1_factor"]["counts"]
+    _, adds, dups = E.plan_stage1(250000)
+    assert (adds, dups) == (g["s1_ptadds"], g["s1_ptdups"])
+
+
+def test_stage1_plan_slot_permutations_are_consistent():
+    # replay the permutation bookkeeping: every op must read slots that hold live points
+    ops, _, _ = E.plan_stage1(5000)
+    perm_tab = [0xE4, 0xB4, 0xD8, 0x78, 0x9C, 0x6C, 0xE1, 0xB1, 0xC9, 0x39, 0x8D, 0x2D,
+                0xD2, 0x72, 0xC6, 0x36, 0x4E, 0x1E, 0x93, 0x63, 0x87, 0x27, 0x4B, 0x1B]
+    live = {0}            # physical slots holding defined points; P starts in slot 0
+    for b in ops:
+        t, p = b & 7, perm_tab[b >> 3]
+        A, B, C, T = p & 3, (p >> 2) & 3, (p >> 4) & 3, (p >> 6) & 3
+        assert len({A, B, C, T}) == 4
+        if t == 0:
+            assert T in live
+        elif t == 1:
+            assert B in live; live = {A, B, C}
+        elif t == 2:
+            assert {A, B, C} <= live; live = {A, B, C, T}
+        elif t in (3, 4, 5):
+            assert {A, B, C} <= live
+        elif t == 6:
+            assert {A, B, C} <= live; live = {T}
+
+
+@pytest.mark.parametrize("lo,hi,b1", [(50000, 5000000, 50000), (3000, 300000, 3000), (1500, 150000, 1500),
+                                      (400, 40000, 400), (200, 20000, 200), (100, 10000, 100), (50, 5000, 50),
+                                      (100002000, 100100000, 2000)])
+def test_pair_matches_oracle(lo, hi, b1):
+    D, U, L, R = E.stage2_params(b1)
+    assert D == O.lib().oracle_stage2_D(b1) and (U, L) == (16, 32)
+    assert E.pair(lo, hi, D) == O.pair(lo, hi, D)
+
+
+def test_pair_counts_match_reference_printout():
+    g = GOLDEN["readme508_b1_5e4"]["counts"]
+    v, u, amin, npairs = E.pair(50000, 5000000, g["D"])
+    assert (len(v), npairs) == (g["pairmap_steps"], g["s2_paired"])
+    D, U, L, R = E.stage2_params(50000)
+    assert (D, U, L, R - 3) == (g["D"], g["U"], g["L"], g["R"])

@@ -1,0 +1,78 @@
+"""GPU parity of curve construction + stage 1 against the golden vectors of the compiled
+reference (byte-identical save_b1.txt lines) and against the oracle, through the C ABI."""
+import pytest
+from conftest import GOLDEN, golden_factor, composites
+import oracle_lib as O
+import avx_ecm_b200 as E
+
+pytestmark = pytest.mark.gpu
+
+MAXBITS = 1024
+
+
+def usable(g):
+    return int(g["n"]).bit_length() <= MAXBITS
+
+
+@pytest.mark.parametrize("name", sorted(k for k, g in GOLDEN.items() if usable(g)))
+def test_stage1_matches_reference_golden(name):
+    g = GOLDEN[name]
+    N, b1 = int(g["n"]), g["b1"]
+    lanes = len(g["save_lines"])
+    r = E.vececm(N, lanes, b1, b2=b1, sigma=int(g["sigma0"]))
+    assert r["save_lines"] == g["save_lines"]
+    assert r["z"] == [int(z, 16) for z in g["z1_true_hex"]]
+    exp = [(int(g["sigma0"]) + i, 1, golden_factor(g, int(g["sigma0"]) + i, 1)) for i in range(lanes)]
+    assert r["factors"] == [e for e in exp if e[2]]
+
+
+def test_curve_construction_matches_oracle():
+    c = composites()
+    for N in (c["syn415"], c["syn1024"], c["t35"], c["small96"]):
+        sig = [6, 7, 1000, 2 ** 32 - 1, 2 ** 32 + 5, 2 ** 63 + 11, 2 ** 64 - 1, 11919771003873180376]
+        ctx = E.EcmContext(N, len(sig))
+        try:
+            ctx.build_curves(sig)
+            x, z, _ = ctx.read_stage1()          # before stage 1: the initial point
+            for s, xi, zi in zip(sig, x, z):
+                ox, _ = O.build_curve(N, s)
+                assert (xi, zi) == (ox, 1)
+        finally:
+            ctx.close()
+
+
+def test_host_loaded_curves_and_ragged_batches():
+    # load_curves path (host-built X, s) and batch sizes that do not fill a block / span blocks
+    N = composites()["syn415"]
+    for count in (1, 33, 321, 700):
+        sig = [100 + i for i in range(count)]
+        built = [O.build_curve(N, s) for s in sig]
+        ctx = E.EcmContext(N, count)
+        try:
+            ctx.load_curves([b[0] for b in built], [b[1] for b in built], sig)
+            ctx.stage1(2000)
+            x1, z1, _ = ctx.read_stage1()
+            ctx.build_curves(sig)
+            ctx.stage1(2000)
+            x2, z2, _ = ctx.read_stage1()
+        finally:
+            ctx.close()
+        assert (x1, z1) == (x2, z2)
+        for i in (0, count // 2, count - 1):
+            r = O.ecm_curve(N, 2000, 2000, sig[i])
+            assert (x1[i], z1[i]) == (r["x"], r["z"])
+
+
+def test_time_sliced_stage1_equals_one_shot():
+    N = composites()["syn415"]
+    sig = list(range(7, 7 + 64))
+    ctx = E.EcmContext(N, len(sig))
+    try:
+        ctx.build_curves(sig); ctx.stage1(50000); a = ctx.read_stage1()
+        ctx.build_curves(sig); ctx.stage1_begin(50000)
+        while not ctx.stage1_step(1):
+            pass
+        ctx.sync(); b = ctx.read_stage1()
+    finally:
+        ctx.close()
+    assert a == b
