@@ -55,6 +55,9 @@ def lib():
         "ecm_b200_stage1_step": (c.c_int, [vp, c.c_uint32, c.POINTER(c.c_int)]),
         "ecm_b200_stage1_launches": (c.c_int, [vp, u32p, u32p]),
         "ecm_b200_sync": (c.c_int, [vp]),
+        "ecm_b200_stage1_progress": (c.c_int, [vp, c.POINTER(c.c_double)]),
+        "ecm_b200_flush_l2": (c.c_int, [vp]),
+        "ecm_b200_timer": (c.c_int, [vp, c.c_int, c.POINTER(c.c_float)]),
         "ecm_b200_read_stage1": (c.c_int, [vp, u32p, u32p, u8p, u32p]),
         "ecm_b200_stage2": (c.c_int, [vp, c.c_uint64, c.c_uint64]),
         "ecm_b200_read_stage2": (c.c_int, [vp, u32p, u8p, u32p, u8p]),
@@ -75,7 +78,7 @@ def lib():
 
 EXPORTS = ["ecm_b200_create", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
            "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
-           "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_read_stage1", "ecm_b200_stage2",
+           "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_stage1_progress", "ecm_b200_flush_l2", "ecm_b200_timer", "ecm_b200_read_stage1", "ecm_b200_stage2",
            "ecm_b200_read_stage2", "ecm_b200_plan_stage1", "ecm_b200_pair", "ecm_b200_stage2_params",
            "ecm_b200_fieldop", "ecm_b200_launch_count", "ecm_b200_last_timing", "ecm_b200_measure_imad_peak"]
 
@@ -169,6 +172,25 @@ class EcmContext:
     def sync(self):
         _check(lib().ecm_b200_sync(self._h))
 
+    def stage1_progress(self):
+        f = ctypes.c_double()
+        _check(lib().ecm_b200_stage1_progress(self._h, ctypes.byref(f)))
+        return f.value
+
+    def timer_start(self):
+        _check(lib().ecm_b200_timer(self._h, 0, None))
+
+    def timer_stop(self):
+        _check(lib().ecm_b200_timer(self._h, 1, None))
+
+    def timer_ms(self):
+        ms = ctypes.c_float()
+        _check(lib().ecm_b200_timer(self._h, 2, ctypes.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        _check(lib().ecm_b200_flush_l2(self._h))
+
     def read_stage1(self):
         """-> (X, Z, factors): residues as written to save_b1.txt and gcd(Z,N) when it is a proper factor."""
         n, nl = self.count, self.nl
@@ -204,6 +226,13 @@ class EcmContext:
         ms, ln = ctypes.c_float(), ctypes.c_uint32()
         _check(lib().ecm_b200_last_timing(self._h, ctypes.byref(ms), ctypes.byref(ln)))
         return ms.value, ln.value
+
+
+def measure_imad_peak(device=0):
+    """-> (32x32->64 products per second, SM clock MHz) of dependency-free IMAD.WIDE chains, measured now."""
+    r, clk = ctypes.c_double(), ctypes.c_double()
+    _check(lib().ecm_b200_measure_imad_peak(device, ctypes.byref(r), ctypes.byref(clk)))
+    return r.value, clk.value
 
 
 def plan_stage1(b1):

@@ -92,12 +92,13 @@ struct ecm_b200_ctx {
     uint32_t max_curves = 0, cap = 0, count = 0, groups = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     uint32_t *d_state = nullptr;
     size_t state_words = 0;
     uint8_t *d_ops = nullptr; size_t d_ops_cap = 0;
     uint32_t *d_io = nullptr; size_t d_io_words = 0;     // staging for host<->device transfers
     void *d_params = nullptr;
+    void *d_flush = nullptr;
     uint8_t *d_flags = nullptr;
     Stage1Plan plan;            // cached for plan.b1
     bool plan_on_device = false;
@@ -170,9 +171,11 @@ void ecm_b200_destroy(ecm_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_state); cudaFree(c->d_ops); cudaFree(c->d_io); cudaFree(c->d_flags); cudaFree(c->d_params);
+    cudaFree(c->d_state); cudaFree(c->d_ops); cudaFree(c->d_io); cudaFree(c->d_flags); cudaFree(c->d_params); cudaFree(c->d_flush);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c->eng;
     delete c;
@@ -296,6 +299,49 @@ int ecm_b200_stage1_launches(const ecm_b200_ctx *c, uint32_t *total, uint32_t *i
     return ECM_B200_OK;
 }
 
+int ecm_b200_stage1_progress(const ecm_b200_ctx *c, double *fraction)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    // every item covers chunk_len ops except those of the last chunk
+    if (fraction) {
+        const uint64_t nops = c->plan.ops.size();
+        if (c->total_items == 0 || nops == 0) { *fraction = 0; return ECM_B200_OK; }
+        const uint64_t full_chunks = c->next_item / c->groups, rest = c->next_item % c->groups;
+        const uint64_t nchunks = c->total_items / c->groups;
+        auto chunk_ops = [&](uint64_t ch) { return ch + 1 < nchunks ? (uint64_t)c->chunk_len : nops - (nchunks - 1) * c->chunk_len; };
+        double done = 0;
+        for (uint64_t ch = 0; ch < full_chunks; ch++) done += (double)chunk_ops(ch) * c->groups;
+        if (rest) done += (double)chunk_ops(full_chunks) * rest;
+        *fraction = done / ((double)nops * c->groups);
+    }
+    return ECM_B200_OK;
+}
+
+int ecm_b200_timer(ecm_b200_ctx *c, int what, float *ms)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
+    if (what == 0) CU(cudaEventRecord(c->ev_t0, c->stream));
+    else if (what == 1) CU(cudaEventRecord(c->ev_t1, c->stream));
+    else {
+        CU(cudaEventSynchronize(c->ev_t1));
+        float t = 0; CU(cudaEventElapsedTime(&t, c->ev_t0, c->ev_t1));
+        if (ms) *ms = t;
+    }
+    return ECM_B200_OK;
+}
+
+int ecm_b200_flush_l2(ecm_b200_ctx *c)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = 256u << 20;
+    if (!c->d_flush) CU(cudaMalloc(&c->d_flush, bytes));
+    CU(cudaMemsetAsync(c->d_flush, (int)(c->launches_issued & 0xff), bytes, c->stream));
+    return ECM_B200_OK;
+}
+
 int ecm_b200_sync(ecm_b200_ctx *c)
 {
     if (!c) return fail(ECM_B200_EINVAL, "null context");
@@ -390,6 +436,5 @@ void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, 
     if (D) *D = p.D; if (U) *U = p.U; if (L) *L = p.L; if (R) *R = p.R;
 }
 
-int ecm_b200_measure_imad_peak(int, double *, double *) { return fail(ECM_B200_ESTATE, "not built yet"); }
 
 }  // extern "C"

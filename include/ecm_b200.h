@@ -61,7 +61,14 @@ int ecm_b200_stage1(ecm_b200_ctx *ctx, uint64_t b1);
 int ecm_b200_stage1_begin(ecm_b200_ctx *ctx, uint64_t b1);
 int ecm_b200_stage1_step(ecm_b200_ctx *ctx, uint32_t max_launches, int *done);
 int ecm_b200_stage1_launches(const ecm_b200_ctx *ctx, uint32_t *total, uint32_t *issued);
+/* fraction of the stage-1 work (ops x curves) enqueued so far, in [0,1] */
+int ecm_b200_stage1_progress(const ecm_b200_ctx *ctx, double *fraction);
 int ecm_b200_sync(ecm_b200_ctx *ctx);
+/* CUDA-event stopwatch on the context's stream: what = 0 record start, 1 record stop, 2 wait for
+ * stop and return the elapsed device time in *ms.                                             */
+int ecm_b200_timer(ecm_b200_ctx *ctx, int what, float *ms);
+/* enqueue a 256 MiB memset on the context's stream (evicts L2 between timed steps) */
+int ecm_b200_flush_l2(ecm_b200_ctx *ctx);
 
 /* Results of stage 1 as the reference writes them to save_b1.txt (ecm.c:1327-1380): X and Z out
  * of Montgomery form, limb-major [limb*count+curve] with ecm_b200_limbs() limbs; factor_flag[i]
