@@ -61,7 +61,9 @@ def lib():
         "ecm_b200_read_stage1": (c.c_int, [vp, u32p, u32p, u8p, u32p]),
         "ecm_b200_stage2": (c.c_int, [vp, c.c_uint64, c.c_uint64]),
         "ecm_b200_read_stage2": (c.c_int, [vp, u32p, u8p, u32p, u8p]),
+        "ecm_b200_stage2_counters": (c.c_int, [vp, u64p, u64p, u64p, u64p]),
         "ecm_b200_plan_stage1": (c.c_uint64, [c.c_uint64, u8p, c.c_uint64, u64p]),
+        "ecm_b200_plan_stage2": (c.c_uint64, [c.c_uint64, c.c_uint64, u64p]),
         "ecm_b200_pair": (c.c_uint32, [c.c_uint64, c.c_uint64, c.c_uint32, c.c_uint32, u32p, u32p, c.c_uint32, u32p, u32p]),
         "ecm_b200_stage2_params": (None, [c.c_uint64, u32p, u32p, u32p, u32p]),
         "ecm_b200_fieldop": (c.c_int, [vp, c.c_int, c.c_uint32, u32p, u32p, u32p, c.c_int]),
@@ -79,7 +81,7 @@ def lib():
 EXPORTS = ["ecm_b200_create", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
            "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
            "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_stage1_progress", "ecm_b200_flush_l2", "ecm_b200_timer", "ecm_b200_read_stage1", "ecm_b200_stage2",
-           "ecm_b200_read_stage2", "ecm_b200_plan_stage1", "ecm_b200_pair", "ecm_b200_stage2_params",
+           "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_pair", "ecm_b200_stage2_params",
            "ecm_b200_fieldop", "ecm_b200_launch_count", "ecm_b200_last_timing", "ecm_b200_measure_imad_peak"]
 
 
@@ -216,6 +218,11 @@ class EcmContext:
         gs = unpack(g, nl, n)
         return unpack(acc, nl, n), [gs[i] if fl[i] else 0 for i in range(n)], list(iv)
 
+    def stage2_counters(self):
+        v = [ctypes.c_uint64() for _ in range(4)]
+        _check(lib().ecm_b200_stage2_counters(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("s2_ptadds", "s2_numinv", "s2_paired", "pairmap_steps"), [x.value for x in v]))
+
     def fieldop(self, op, a, b, repeat=1):
         n, nl = len(a), self.nl
         r = (ctypes.c_uint32 * (nl * n))()
@@ -243,6 +250,14 @@ def plan_stage1(b1):
     buf = (ctypes.c_uint8 * max(1, n))()
     L.ecm_b200_plan_stage1(b1, buf, n, cnt)
     return bytes(buf[:n]), cnt[0], cnt[1]
+
+
+def plan_stage2(b1, b2):
+    """Compile (not run) the stage-2 program; -> dict of the reference's counters + program length."""
+    cnt = (ctypes.c_uint64 * 6)()
+    n = lib().ecm_b200_plan_stage2(b1, b2, cnt)
+    return {"instructions": n, "s2_ptadds": cnt[0], "s2_numinv": cnt[1], "s2_paired": cnt[2], "pairmap_steps": cnt[3],
+            "last_amin": cnt[4], "table_entries": cnt[5]}
 
 
 def pair(lo, hi, D, U=16):

@@ -4,6 +4,7 @@
 #include "../../include/ecm_b200.h"
 #include "engine.hpp"
 #include "plan.hpp"
+#include "plan2.hpp"
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdio>
@@ -107,6 +108,11 @@ struct ecm_b200_ctx {
     int p_slot = 0;             // physical point slot holding P
     bool have_curves = false, stage1_done = false;
     float last_ms = 0; uint32_t last_launches = 0;
+    // stage 2
+    Stage2Program prog2; uint64_t prog2_b1 = 0, prog2_b2 = 0;
+    uint32_t *d_acc = nullptr; uint8_t *d_fail = nullptr;       // per batch curve: accumulator (Montgomery form), inversion-failure flag
+    bool stage2_done = false;
+    float s2_ms = 0; uint32_t s2_launches = 0; uint32_t s2_waves = 0;
 };
 
 extern "C" {
@@ -171,7 +177,7 @@ void ecm_b200_destroy(ecm_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_state); cudaFree(c->d_ops); cudaFree(c->d_io); cudaFree(c->d_flags); cudaFree(c->d_params); cudaFree(c->d_flush);
+    cudaFree(c->d_state); cudaFree(c->d_ops); cudaFree(c->d_io); cudaFree(c->d_flags); cudaFree(c->d_params); cudaFree(c->d_flush); cudaFree(c->d_acc); cudaFree(c->d_fail);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -389,8 +395,116 @@ int ecm_b200_read_stage1(ecm_b200_ctx *c, uint32_t *x, uint32_t *z, uint8_t *fac
     return ECM_B200_OK;
 }
 
-int ecm_b200_stage2(ecm_b200_ctx *, uint64_t, uint64_t) { return fail(ECM_B200_ESTATE, "stage 2 not built yet"); }
-int ecm_b200_read_stage2(ecm_b200_ctx *, uint32_t *, uint8_t *, uint32_t *, uint8_t *) { return fail(ECM_B200_ESTATE, "stage 2 not built yet"); }
+// Run one compiled stage-2 program over a wave of `groups` curve groups with the same round-robin
+// (group, chunk) schedule as stage 1.
+static int run_program(ecm_b200_ctx *c, const uint64_t *d_code, uint64_t ncode, uint32_t *state2, uint32_t cap2, uint32_t *tab,
+                       uint32_t groups, uint8_t *inv_fail)
+{
+    const uint32_t chunk = 65536;
+    const uint64_t nchunks = (ncode + chunk - 1) / chunk;
+    const uint64_t items = nchunks * groups;
+    const uint32_t per = std::min<uint32_t>(groups, (uint32_t)c->num_sms);
+    for (uint64_t it = 0; it < items;) {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>(per, items - it);
+        c->eng->vm2(c->stream, blocks, state2, cap2, tab, d_code, ncode, chunk, groups, it, inv_fail);
+        c->s2_launches++;
+        it += blocks;
+    }
+    CU(cudaGetLastError());
+    return ECM_B200_OK;
+}
+
+int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (!c->have_curves) return fail(ECM_B200_ESTATE, "no curves loaded");
+    if (b2 <= b1) return fail(ECM_B200_EINVAL, "B2 must exceed B1 (B2 <= B1 disables stage 2, main.c:548-552)");
+    CU(cudaSetDevice(c->device));
+    // ---- compile (host): ecm_stage2_init + one ecm_stage2_pair program per 1e8 prime range (ecm.c:1424-1476)
+    if (c->prog2_b1 != b1 || c->prog2_b2 != b2) {
+        plan_stage2_init(b1, c->prog2);
+        const uint64_t PRIME_RANGE = 100000000ull;
+        for (uint64_t p = b1; p < b2; p += PRIME_RANGE) plan_stage2_range(p, std::min(p + PRIME_RANGE, b2), c->prog2);
+        c->prog2_b1 = b1; c->prog2_b2 = b2;
+    }
+    const Stage2Program &pg = c->prog2;
+    const int nl = c->nl;
+    const uint32_t T = c->eng->threads_s2;
+    // ---- wave size from the memory budget: tables + slot file per curve
+    const size_t per_curve = ((size_t)pg.lay.entries + c->eng->nslot_s2) * nl * 4 + 1;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t code_bytes = pg.init.size() * 8;
+    for (const auto &r : pg.ranges) code_bytes = std::max(code_bytes, r.size() * 8);
+    const size_t budget = (size_t)((double)free_b * 0.90) - std::min<size_t>(code_bytes + (64u << 20), free_b / 4);
+    uint32_t cap2 = (uint32_t)std::min<size_t>((c->count + T - 1) / T * T, budget / per_curve / T * T);
+    if (cap2 < T) return fail(ECM_B200_ENOMEM, "not enough device memory for one stage-2 group");
+    uint32_t *tab = nullptr, *state2 = nullptr; uint8_t *wfail = nullptr; uint64_t *d_code = nullptr;
+    auto cleanup = [&]() { cudaFree(tab); cudaFree(state2); cudaFree(wfail); cudaFree(d_code); };
+#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ECM_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    CUS(cudaMalloc(&tab, (size_t)pg.lay.entries * nl * 4 * cap2));
+    CUS(cudaMalloc(&state2, (size_t)c->eng->nslot_s2 * nl * 4 * cap2));
+    CUS(cudaMalloc(&wfail, cap2));
+    CUS(cudaMalloc(&d_code, code_bytes + 64));
+    if (!c->d_acc) { CUS(cudaMalloc(&c->d_acc, (size_t)nl * 4 * c->max_curves)); CUS(cudaMalloc(&c->d_fail, c->max_curves)); }
+    c->s2_launches = 0; c->s2_waves = 0;
+    CUS(cudaEventRecord(c->ev0, c->stream));
+    for (uint32_t first = 0; first < c->count; first += cap2) {
+        const uint32_t n = std::min<uint32_t>(cap2, c->count - first);
+        const uint32_t groups = (n + T - 1) / T;
+        c->eng->s2_setup(c->stream, c->d_state, c->cap, 2 * c->p_slot, 2 * c->p_slot + 1, SP, first, c->count, state2, cap2, tab,
+                         pg.lay.qx, pg.lay.qz, wfail);
+        CUS(cudaMemcpyAsync(d_code, pg.init.data(), pg.init.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        int rc = run_program(c, d_code, pg.init.size(), state2, cap2, tab, groups, wfail);
+        if (rc) { cleanup(); return rc; }
+        for (const auto &r : pg.ranges) {
+            CUS(cudaMemcpyAsync(d_code, r.data(), r.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            rc = run_program(c, d_code, r.size(), state2, cap2, tab, groups, wfail);
+            if (rc) { cleanup(); return rc; }
+        }
+        c->eng->s2_collect(c->stream, state2, cap2, wfail, first, n, c->count, c->d_acc, c->d_fail);
+        c->s2_waves++;
+    }
+    CUS(cudaEventRecord(c->ev1, c->stream));
+    CUS(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->s2_ms, c->ev0, c->ev1);
+    c->last_ms = c->s2_ms; c->last_launches = c->s2_launches;
+#undef CUS
+    cleanup();
+    c->stage2_done = true;
+    return ECM_B200_OK;
+}
+
+int ecm_b200_read_stage2(ecm_b200_ctx *c, uint32_t *acc, uint8_t *factor_flag, uint32_t *gcd_out, uint8_t *inv_fail)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (!c->stage2_done) return fail(ECM_B200_ESTATE, "stage 2 has not been run");
+    CU(cudaSetDevice(c->device));
+    const size_t words = (size_t)c->nl * c->count;
+    uint32_t *da = c->d_io, *dg = c->d_io + words;
+    const bool want_flag = factor_flag || gcd_out;
+    // d_acc is laid out like a one-slot state with cap = count
+    c->eng->read_point(c->stream, c->d_acc, c->count, c->count, 0, 0, nullptr, da, want_flag ? c->d_flags : nullptr,
+                       gcd_out ? dg : nullptr);
+    CU(cudaGetLastError());
+    if (acc) CU(cudaMemcpyAsync(acc, da, words * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (factor_flag) CU(cudaMemcpyAsync(factor_flag, c->d_flags, c->count, cudaMemcpyDeviceToHost, c->stream));
+    if (gcd_out) CU(cudaMemcpyAsync(gcd_out, dg, words * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (inv_fail) CU(cudaMemcpyAsync(inv_fail, c->d_fail, c->count, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return ECM_B200_OK;
+}
+
+// counters of the compiled stage-2 program (what the reference prints, ecm.c:1481-1483)
+int ecm_b200_stage2_counters(const ecm_b200_ctx *c, uint64_t *ptadds, uint64_t *numinv, uint64_t *paired, uint64_t *steps)
+{
+    if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (ptadds) *ptadds = c->prog2.ptadds;
+    if (numinv) *numinv = c->prog2.numinv;
+    if (paired) *paired = c->prog2.paired;
+    if (steps) *steps = c->prog2.pairmap_steps;
+    return ECM_B200_OK;
+}
 
 int ecm_b200_fieldop(ecm_b200_ctx *c, int op, uint32_t count, const uint32_t *a, const uint32_t *b, uint32_t *r, int repeat)
 {
@@ -428,6 +542,17 @@ uint32_t ecm_b200_pair(uint64_t lo, uint64_t hi, uint32_t D, uint32_t U, uint32_
     uint32_t steps = pair_plan(lo, hi, p, v, u, amin_final, npairs);
     if (pairmap_v && pairmap_u && cap >= steps) { memcpy(pairmap_v, v.data(), steps * 4ull); memcpy(pairmap_u, u.data(), steps * 4ull); }
     return steps;
+}
+
+uint64_t ecm_b200_plan_stage2(uint64_t b1, uint64_t b2, uint64_t *counts)
+{
+    Stage2Program pg;
+    plan_stage2_init(b1, pg);
+    for (uint64_t p = b1; p < b2; p += 100000000ull) plan_stage2_range(p, std::min<uint64_t>(p + 100000000ull, b2), pg);
+    uint64_t n = pg.init.size();
+    for (const auto &r : pg.ranges) n += r.size();
+    if (counts) { counts[0] = pg.ptadds; counts[1] = pg.numinv; counts[2] = pg.paired; counts[3] = pg.pairmap_steps; counts[4] = pg.last_amin; counts[5] = pg.lay.entries; }
+    return n;
 }
 
 void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R)

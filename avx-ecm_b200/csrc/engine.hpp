@@ -23,6 +23,15 @@ struct Engine {
     virtual void build_curves(cudaStream_t st, uint32_t *state, uint32_t cap, uint32_t count, const uint32_t *uv, uint8_t *ok) = 0;
     virtual void read_point(cudaStream_t st, const uint32_t *state, uint32_t cap, uint32_t count, uint32_t xs, uint32_t zs,
                             uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g) = 0;
+    // stage 2
+    int threads_s2 = 0, smem_s2 = 0, nslot_s2 = 0;
+    virtual void vm2(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, uint32_t *tab, const uint64_t *code,
+                     uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0, uint8_t *inv_fail) = 0;
+    virtual void s2_setup(cudaStream_t st, const uint32_t *state1, uint32_t cap1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
+                          uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab, uint32_t e_qx,
+                          uint32_t e_qz, uint8_t *inv_fail) = 0;
+    virtual void s2_collect(cudaStream_t st, const uint32_t *state2, uint32_t cap2, const uint8_t *inv_fail, uint32_t first,
+                            uint32_t n, uint32_t count, uint32_t *acc_out, uint8_t *fail_out) = 0;
     virtual void fieldop(cudaStream_t st, int op, uint32_t count, const uint32_t *a, const uint32_t *b, uint32_t *r, int repeat) = 0;
 };
 

@@ -16,6 +16,7 @@ struct EngineT : Engine {
     {
         nl = NL; threads_s1 = BlockCfg<NL, NSLOT_S1>::THREADS; smem_s1 = BlockCfg<NL, NSLOT_S1>::smem;
         params_bytes = sizeof(ModParams<NL>);
+        threads_s2 = BlockCfg<NL, NSLOT_S2>::THREADS; smem_s2 = BlockCfg<NL, NSLOT_S2>::smem; nslot_s2 = NSLOT_S2;
     }
     void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, uint32_t m0inv) override
     {
@@ -26,7 +27,28 @@ struct EngineT : Engine {
     void set_params_device(const void *d) override { Pg = static_cast<const ModParams<NL> *>(d); }
     cudaError_t prepare() override
     {
-        return cudaFuncSetAttribute(k_stage1<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s1);
+        cudaError_t e = cudaFuncSetAttribute(k_stage1<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s1);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k_vm2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
+    }
+    void vm2(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, uint32_t *tab, const uint64_t *code,
+             uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0, uint8_t *inv_fail) override
+    {
+        k_vm2<NL><<<blocks, threads_s2, smem_s2, st>>>(P, Pg, state2, cap, tab, code, ncode, chunk_len, groups, item0, inv_fail);
+        count_launch();
+    }
+    void s2_setup(cudaStream_t st, const uint32_t *state1, uint32_t cap1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
+                  uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab, uint32_t e_qx, uint32_t e_qz,
+                  uint8_t *inv_fail) override
+    {
+        k_s2_setup<NL><<<(cap2 + 127) / 128, 128, 0, st>>>(state1, cap1, xslot, zslot, spslot, first, count, state2, cap2, tab, e_qx, e_qz, inv_fail);
+        count_launch();
+    }
+    void s2_collect(cudaStream_t st, const uint32_t *state2, uint32_t cap2, const uint8_t *inv_fail, uint32_t first, uint32_t n,
+                    uint32_t count, uint32_t *acc_out, uint8_t *fail_out) override
+    {
+        k_s2_collect<NL><<<(n + 127) / 128, 128, 0, st>>>(state2, cap2, inv_fail, first, n, count, acc_out, fail_out);
+        count_launch();
     }
     void stage1(cudaStream_t st, uint32_t blocks, uint32_t *state, uint32_t cap, const uint8_t *ops, uint64_t nops,
                 uint32_t chunk_len, uint32_t groups, uint64_t item0) override

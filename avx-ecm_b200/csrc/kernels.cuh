@@ -229,4 +229,131 @@ __global__ void k_fieldop(const ModParams<NL> P, const ModParams<NL> *Pg, int op
     for (int k = 0; k < NL; k++) r_out[(size_t)k * count + c] = r[k];
 }
 
+// =================================================================================================
+// stage 2: the second field-op machine.  Same execution model as stage 1 (one thread = one curve,
+// slot file in shared memory, one op stream for the whole batch) with 64-bit instructions
+// compiled by plan2.cpp, global-memory point tables, a modular inverse and the fused pair step.
+// Table entry e of curve c: tab[(e*NL + limb)*cap + c].
+// =================================================================================================
+enum : uint32_t { V2_MUL = 0, V2_SQR = 1, V2_ADD = 2, V2_SUB = 3, V2_ADDSUB = 4, V2_COPY = 5, V2_LDG = 6, V2_STG = 7,
+                  V2_INV = 8, V2_ONE = 9, V2_PAIR = 10, V2_NOP = 11 };
+enum : uint32_t { V2_SP = 10, V2_ACC = 11, NSLOT_S2 = 14 };
+
+// d = 1/x (both Montgomery form).  Non-invertible x: reproduce what lane 0 of the reference's
+// vectors does (ecm.c:1925-1949 with insert_mpz_to_vec main.c:117-138): the accumulator becomes the
+// raw gcd and the "inverse" is the raw, un-inverted product -- as Montgomery-domain values of the
+// reference (R_ref = 2^MAXBITS) these are g/R_ref and x/R_ref.
+template <int NL, int THREADS>
+__device__ __noinline__ void vm2_inverse(uint32_t *smem_thread, uint32_t d, uint32_t x, const ModParams<NL> *Pg, uint8_t *fail_flag)
+{
+    uint32_t a[NL], inv[NL], g[NL], t[NL];
+    for (int k = 0; k < NL; k++) a[k] = smem_thread[(x * NL + k) * THREADS];
+    const bool ok = nm_inverse<NL>(inv, g, a, Pg);
+    if (ok) {
+        nm_mul<NL>(t, inv, Pg->r3, Pg);                   // (xR)^-1 * R^3 * R^-1 = x^-1 R
+    } else {
+        *fail_flag = 1;
+        nm_mul<NL>(t, g, Pg->r2, Pg);                     // g in Montgomery form
+        nm_mul<NL>(t, t, Pg->rrefinv, Pg);                // g / R_ref
+        for (int k = 0; k < NL; k++) smem_thread[(V2_ACC * NL + k) * THREADS] = t[k];
+        nm_mul<NL>(t, a, Pg->rrefinv, Pg);                // x / R_ref
+    }
+    for (int k = 0; k < NL; k++) smem_thread[(d * NL + k) * THREADS] = t[k];
+}
+
+template <int NL>
+__global__ void __launch_bounds__(BlockCfg<NL, NSLOT_S2>::THREADS, 1)
+k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ state2, uint32_t cap, uint32_t *__restrict__ tab,
+      const uint64_t *__restrict__ code, uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0,
+      uint8_t *__restrict__ inv_fail)
+{
+    constexpr int THREADS = BlockCfg<NL, NSLOT_S2>::THREADS;
+    extern __shared__ uint32_t smem[];
+    const uint64_t item = item0 + blockIdx.x;
+    const uint32_t g = (uint32_t)(item % groups);
+    const uint64_t chunk = item / groups;
+    const uint32_t curve = g * THREADS + threadIdx.x;
+    Slots<NL, THREADS> S{smem + threadIdx.x};
+    uint32_t a[NL], b[NL], r[NL];
+#pragma unroll 1
+    for (uint32_t s = 0; s < NSLOT_S2; s++) { gload<NL>(r, state2, cap, s, curve); S.store(s, r); }
+
+    uint64_t i = chunk * chunk_len;
+    const uint64_t end = (i + chunk_len < ncode) ? i + chunk_len : ncode;
+#pragma unroll 1
+    for (; i < end; i++) {
+        const uint64_t ins = __ldg(code + i);
+        const uint32_t lo = (uint32_t)ins, imm = (uint32_t)(ins >> 32);
+        const uint32_t op = lo & 0xffu, d = (lo >> 8) & 0xffu, x = (lo >> 16) & 0xffu, y = lo >> 24;
+        if (op <= V2_SQR || op == V2_PAIR) {
+            uint32_t dst = d;
+            if (op == V2_PAIR) {                         // acc *= Pa_inv[pa] - Pb[pb].X  (ecm.c:1857-1859)
+                uint32_t u[NL], v[NL];
+                gload<NL>(u, tab, cap, imm & 0xffffu, curve);
+                gload<NL>(v, tab, cap, imm >> 16, curve);
+                mod_sub<NL>(a, u, v, P);
+                S.load(b, V2_ACC);
+                dst = V2_ACC;
+            } else {
+                S.load(a, x);
+                S.load(b, y);
+            }
+            mont_mul<NL>(r, a, b, P);
+            S.store(dst, r);
+        } else if (op == V2_ADDSUB) {
+            S.load(a, x); S.load(b, y);
+            mod_add<NL>(r, a, b, P); S.store(d, r);
+            mod_sub<NL>(r, a, b, P); S.store(imm, r);
+        } else if (op == V2_ADD) {
+            S.load(a, x); S.load(b, y); mod_add<NL>(r, a, b, P); S.store(d, r);
+        } else if (op == V2_SUB) {
+            S.load(a, x); S.load(b, y); mod_sub<NL>(r, a, b, P); S.store(d, r);
+        } else if (op == V2_COPY) {
+            S.load(a, x); S.store(d, a);
+        } else if (op == V2_LDG) {
+            gload<NL>(a, tab, cap, imm, curve); S.store(d, a);
+        } else if (op == V2_STG) {
+            S.load(a, x); gstore<NL>(tab, cap, imm, curve, a);
+        } else if (op == V2_INV) {
+            vm2_inverse<NL, THREADS>(smem + threadIdx.x, d, x, Pg, inv_fail + curve);
+        } else if (op == V2_ONE) {
+#pragma unroll
+            for (int k = 0; k < NL; k++) a[k] = P.one[k];
+            S.store(d, a);
+        }
+    }
+#pragma unroll 1
+    for (uint32_t s = 0; s < NSLOT_S2; s++) { S.load(r, s); gstore<NL>(state2, cap, s, curve, r); }
+}
+
+// stage-2 wave set-up: Q = stage-1 result and the curve parameter move from the stage-1 state into
+// the wave's table / slot file.  Wave curve c is batch curve first + c (clamped: padding lanes repeat
+// the last curve).
+template <int NL>
+__global__ void k_s2_setup(const uint32_t *state1, uint32_t cap1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
+                           uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab,
+                           uint32_t e_qx, uint32_t e_qz, uint8_t *inv_fail)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cap2) return;
+    uint32_t src = first + c; if (src >= count) src = count - 1;
+    for (int k = 0; k < NL; k++) {
+        tab[((size_t)e_qx * NL + k) * cap2 + c] = state1[((size_t)xslot * NL + k) * cap1 + src];
+        tab[((size_t)e_qz * NL + k) * cap2 + c] = state1[((size_t)zslot * NL + k) * cap1 + src];
+        for (uint32_t s = 0; s < NSLOT_S2; s++)
+            state2[((size_t)s * NL + k) * cap2 + c] = (s == V2_SP) ? state1[((size_t)spslot * NL + k) * cap1 + src] : 0;
+    }
+    inv_fail[c] = 0;
+}
+// collect the accumulators (and failure flags) of a finished wave into batch-indexed arrays
+template <int NL>
+__global__ void k_s2_collect(const uint32_t *state2, uint32_t cap2, const uint8_t *inv_fail, uint32_t first, uint32_t n,
+                             uint32_t count, uint32_t *acc_out, uint8_t *fail_out)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    for (int k = 0; k < NL; k++) acc_out[(size_t)k * count + first + c] = state2[((size_t)V2_ACC * NL + k) * cap2 + c];
+    fail_out[first + c] = inv_fail[c];
+}
+
 }  // namespace ecmb200

@@ -1,0 +1,262 @@
+// plan2.cpp -- stage-2 program generator (see plan2.hpp).  Own implementation; the emitted field-op
+// sequence is the one the reference executes in ecm_stage2_init (ecm.c:2201-2340),
+// batch_invert_pt_inplace / batch_invert_pt_to_bignum (ecm.c:1869-2136), next_pt_vec
+// (ecm.c:886-976) and ecm_stage2_pair (ecm.c:2342-2540), so residues are identical.
+#include "plan2.hpp"
+#include <algorithm>
+
+namespace ecmb200 {
+
+namespace {
+
+struct Pt { uint32_t x, z; };
+const Pt PU{UX, UZ}, PV{VX, VZ}, PW{WX, WZ};
+
+struct Asm {
+    std::vector<uint64_t> &code;
+    void put(uint32_t op, uint32_t d, uint32_t x, uint32_t y, uint32_t imm = 0)
+    {
+        code.push_back((uint64_t)(op | (d << 8) | (x << 16) | (y << 24)) | ((uint64_t)imm << 32));
+    }
+    void mul(uint32_t d, uint32_t x, uint32_t y) { put(V_MUL, d, x, y); }
+    void sqr(uint32_t d, uint32_t x) { put(V_SQR, d, x, x); }
+    void add(uint32_t d, uint32_t x, uint32_t y) { put(V_ADD, d, x, y); }
+    void sub(uint32_t d, uint32_t x, uint32_t y) { put(V_SUB, d, x, y); }
+    void addsub(uint32_t dsum, uint32_t ddiff, uint32_t x, uint32_t y) { put(V_ADDSUB, dsum, x, y, ddiff); }
+    void copy(uint32_t d, uint32_t x) { put(V_COPY, d, x, 0); }
+    void ldg(uint32_t d, uint32_t entry) { put(V_LDG, d, 0, 0, entry); }
+    void stg(uint32_t x, uint32_t entry) { put(V_STG, 0, x, 0, entry); }
+    void inv(uint32_t d, uint32_t x) { put(V_INV, d, x, 0); }
+    void one(uint32_t d) { put(V_ONE, d, 0, 0); }
+    void pair(uint32_t e_pa, uint32_t e_pb) { put(V_PAIR, 0, 0, 0, e_pa | (e_pb << 16)); }
+    void ldpt(Pt p, uint32_t ex, uint32_t ez) { ldg(p.x, ex); ldg(p.z, ez); }
+    void stpt(Pt p, uint32_t ex, uint32_t ez) { stg(p.x, ex); stg(p.z, ez); }
+
+    // sums/differences of a point into one of the two pairs
+    void sums1(Pt p) { addsub(S1_, D1_, p.x, p.z); }
+    void sums2(Pt p) { addsub(S2_, D2_, p.x, p.z); }
+
+    // vec_add (ecm.c:407-443): uses (s1,d1) and (s2,d2); clobbers s1,d1 (they hold the temporaries),
+    // leaves s2,d2 intact.  out must differ from in.
+    void vadd(Pt in, Pt out)
+    {
+        mul(D1_, D1_, S2_);
+        mul(S1_, S1_, D2_);
+        addsub(D1_, S1_, D1_, S1_);
+        sqr(D1_, D1_);
+        sqr(S1_, S1_);
+        mul(out.x, D1_, in.z);
+        mul(out.z, S1_, in.x);
+    }
+    // same operation with the roles of the two pairs exchanged (identical values: the only change
+    // is the sign of the squared difference); clobbers s2,d2, leaves s1,d1 intact.
+    void vadd_swapped(Pt in, Pt out)
+    {
+        mul(D2_, D2_, S1_);
+        mul(S2_, S2_, D1_);
+        addsub(D2_, S2_, D2_, S2_);
+        sqr(D2_, D2_);
+        sqr(S2_, S2_);
+        mul(out.x, D2_, in.z);
+        mul(out.z, S2_, in.x);
+    }
+    // vec_duplicate (ecm.c:445-457) from sums (s,d); tmp is any dead slot; clobbers s,d
+    void vdup(uint32_t s, uint32_t d, uint32_t tmp, Pt out)
+    {
+        sqr(d, d);
+        sqr(s, s);
+        mul(out.x, d, s);
+        sub(tmp, s, d);
+        mul(s, tmp, SP_);
+        add(s, s, d);
+        mul(out.z, s, tmp);
+    }
+};
+
+// next_pt_vec (ecm.c:886-976): [c]Q by the binary ladder.  Q is read from the table, the result is
+// left in point slot PU.  x1 = PU, x2 = PV, PW = Q.
+void ladder(Asm &a, const Stage2Layout &L, uint64_t c, uint64_t &ptadds)
+{
+    a.ldpt(PU, L.qx, L.qz);
+    if (c == 1) return;
+    a.sums1(PU);
+    a.vdup(S1_, D1_, T1_, PV);                     // x2 = 2Q
+    if (c == 2) { a.copy(UX, VX); a.copy(UZ, VZ); return; }
+    a.ldpt(PW, L.qx, L.qz);
+    for (int bit = 62 - __builtin_clzll(c); bit >= 0; bit--) {
+        if ((c >> bit) & 1) {                      // x1 = x1 + x2 (Q) ; x2 = 2 x2
+            a.sums2(PV);
+            a.sums1(PU);
+            a.vadd(PW, PU);
+            a.vdup(S2_, D2_, T1_, PV);
+        } else {                                   // x2 = x1 + x2 (Q) ; x1 = 2 x1
+            a.sums1(PV);
+            a.sums2(PU);
+            a.vadd(PW, PV);
+            a.vdup(S2_, D2_, T1_, PU);
+        }
+        ptadds++;
+    }
+}
+
+// Montgomery's simultaneous inversion (batch_invert_pt_*, ecm.c:1869-2136) over table entries
+// zs[0..n): out[i] = x[i] / z[i].  Prefix products go to the table `pref`; the running suffix
+// inverse lives in slot T1.
+void batch_invert(Asm &a, const std::vector<uint32_t> &xs, const std::vector<uint32_t> &zs,
+                  const std::vector<uint32_t> &outs, uint32_t pref)
+{
+    const size_t n = zs.size();
+    a.ldg(T1_, zs[0]);
+    a.stg(T1_, pref);
+    for (size_t i = 1; i < n; i++) {               // A[i] = z[i] * A[i-1]
+        a.ldg(T2_, zs[i]);
+        a.mul(T1_, T2_, T1_);
+        a.stg(T1_, pref + (uint32_t)i);
+    }
+    a.inv(T1_, T1_);                               // B[n-1]
+    for (size_t i = n - 1; i >= 1; i--) {
+        a.ldg(T2_, pref + (uint32_t)i - 1);
+        a.mul(T2_, T1_, T2_);                      // 1/z[i] = B[i] * A[i-1]
+        a.ldg(S1_, xs[i]);
+        a.mul(S1_, S1_, T2_);
+        a.stg(S1_, outs[i]);
+        a.ldg(T2_, zs[i]);
+        a.mul(T1_, T2_, T1_);                      // B[i-1] = z[i] * B[i]
+    }
+    a.ldg(S1_, xs[0]);
+    a.mul(S1_, S1_, T1_);
+    a.stg(S1_, outs[0]);
+}
+
+}  // namespace
+
+Stage2Layout stage2_layout(const Stage2Params &p)
+{
+    Stage2Layout L;
+    uint32_t stored = 0;
+    stage2_map(p, &stored);
+    L.npb = stored;
+    const uint32_t win = 2 * p.L;
+    uint32_t e = 0;
+    L.pbx = e; e += L.npb;
+    L.pai = e; e += win;           // keep the two tables the pair loop reads below 2^16
+    L.pbz = e; e += L.npb;
+    L.pba = e; e += L.npb;
+    L.pax = e; e += win;
+    L.paz = e; e += win;
+    L.paa = e; e += win;
+    L.qx = e++; L.qz = e++; L.pdx = e++; L.pdz = e++;
+    L.entries = e;
+    return L;
+}
+
+// ecm_stage2_init (ecm.c:2201-2340)
+void plan_stage2_init(uint64_t b1, Stage2Program &prog)
+{
+    prog.prm = stage2_params(b1);
+    prog.lay = stage2_layout(prog.prm);
+    prog.init.clear(); prog.ranges.clear();
+    prog.ptadds = prog.numinv = prog.paired = prog.pairmap_steps = 0;
+    const Stage2Params &p = prog.prm;
+    const Stage2Layout &L = prog.lay;
+    const std::vector<uint32_t> map = stage2_map(p, nullptr);
+    Asm a{prog.init};
+
+    // Pb[1] = Q ; Pb[2] = 2Q
+    a.ldpt(PV, L.qx, L.qz);
+    a.stpt(PV, L.pbx + 1, L.pbz + 1);
+    a.sums1(PV);
+    a.sums2(PV);                                   // (s2,d2) = sums of S1 = Q, constant during the build
+    a.vdup(S1_, D1_, T1_, PU);
+    a.stpt(PU, L.pbx + 2, L.pbz + 2);
+    // running points: P1 = S_{j-1} (slot U), P3 = S_{j-2} (slot V), Pout (slot W); rotate names
+    Pt P1 = PU, P3 = PV, Pout = PW;
+    uint32_t last = 2;
+    for (uint32_t j = 3; j <= p.U * p.D; j++) {
+        a.sums1(P1);
+        a.vadd(P3, Pout);                          // S_j = S_{j-1} + S_1, difference S_{j-2}
+        prog.ptadds++;
+        if (map[j] > 0) { a.stpt(Pout, L.pbx + map[j], L.pbz + map[j]); last = map[j]; }
+        Pt t = P3; P3 = P1; P1 = Pout; Pout = t;
+    }
+    a.one(ACC);                                    // acc = one (ecm.c:2318)
+    // batch_invert_pt_inplace(Pb, ..., last+1): entries 1..last
+    {
+        std::vector<uint32_t> xs, zs;
+        for (uint32_t i = 1; i <= last; i++) { xs.push_back(L.pbx + i); zs.push_back(L.pbz + i); }
+        batch_invert(a, xs, zs, xs, L.pba);
+        prog.numinv++;
+    }
+    // Pd = [w]Q
+    ladder(a, L, p.D, prog.ptadds);
+    a.stpt(PU, L.pdx, L.pdz);
+}
+
+// ecm_stage2_pair (ecm.c:2342-2540) for the primes of [lo,hi)
+void plan_stage2_range(uint64_t lo, uint64_t hi, Stage2Program &prog)
+{
+    const Stage2Params &p = prog.prm;
+    const Stage2Layout &L = prog.lay;
+    const std::vector<uint32_t> map = stage2_map(p, nullptr);
+    const uint32_t w = p.D, U = p.U, win = 2 * p.L;
+    prog.ranges.emplace_back();
+    Asm a{prog.ranges.back()};
+
+    std::vector<uint32_t> pm_v, pm_u;
+    uint32_t amin_final = 0, npairs = 0;
+    const uint32_t steps = pair_plan(lo, hi, p, pm_v, pm_u, &amin_final, &npairs);
+    prog.pairmap_steps += steps;
+
+    uint32_t amin = (uint32_t)((lo + w) / (2 * (uint64_t)w));
+    const uint64_t A = (uint64_t)amin * w * 2;
+    // the window is a ring of `win` table entries: logical index i lives at ring[(base+i) % win]
+    uint32_t base = 0;
+    auto ring = [&](uint32_t i) { return (base + i) % win; };
+
+    // Pa[0] = [A]Q, Pad = [A-w]Q, Pa[1] = Pa[0] + Pd (Pad)
+    ladder(a, L, A, prog.ptadds);
+    a.stpt(PU, L.pax + ring(0), L.paz + ring(0));
+    ladder(a, L, A - w, prog.ptadds);              // Pad in slot U
+    a.copy(WX, UX); a.copy(WZ, UZ);                // Pad -> W
+    a.ldpt(PV, L.pax + ring(0), L.paz + ring(0));  // Pa[0] -> V
+    a.ldpt(PU, L.pdx, L.pdz);
+    a.sums2(PU);                                   // (s2,d2) = sums of Pd, constant below
+    a.sums1(PV);
+    a.vadd(PW, PU);                                // Pa[1] -> U
+    prog.ptadds++;
+    a.stpt(PU, L.pax + ring(1), L.paz + ring(1));
+    // chain: cur = Pa[i-1] (U), prev = Pa[i-2] (V), out (W)
+    Pt cur = PU, prev = PV, out = PW;
+    auto extend = [&](uint32_t i) {
+        a.sums1(cur);
+        a.vadd(prev, out);
+        prog.ptadds++;
+        a.stpt(out, L.pax + ring(i), L.paz + ring(i));
+        Pt t = prev; prev = cur; cur = out; out = t;
+    };
+    auto invert = [&](uint32_t from, uint32_t to) {
+        std::vector<uint32_t> xs, zs, outs;
+        for (uint32_t i = from; i < to; i++) { xs.push_back(L.pax + ring(i)); zs.push_back(L.paz + ring(i)); outs.push_back(L.pai + ring(i)); }
+        batch_invert(a, xs, zs, outs, L.paa);
+        prog.numinv++;
+    };
+    for (uint32_t i = 2; i < win; i++) extend(i);
+    invert(0, win);
+    prog.numinv++;                                 // the reference counts this one twice (ecm.c:2429)
+
+    for (uint32_t k = 0; k < steps; k++) {
+        if (pm_u[k] == 0 && pm_v[k] == 0) {        // slide the window by 2U points (ecm.c:2458-2502)
+            base = (base + 2 * U) % win;
+            for (uint32_t i = win - 2 * U; i < win; i++) extend(i);
+            amin += U;
+            invert(win - 2 * U, win);
+        } else {
+            const uint32_t pa = pm_v[k] - amin, pb = pm_u[k];
+            a.pair(L.pai + ring(pa), L.pbx + map[pb]);
+            prog.paired++;
+        }
+    }
+    prog.last_amin = amin;
+}
+
+}  // namespace ecmb200

@@ -84,6 +84,9 @@ int ecm_b200_stage2(ecm_b200_ctx *ctx, uint64_t b1, uint64_t b2);
  * (ecm.c:1485-1497); inv_fail[i] = 1 when curve i met a non-invertible element.                */
 int ecm_b200_read_stage2(ecm_b200_ctx *ctx, uint32_t *acc, uint8_t *factor_flag, uint32_t *gcd_out, uint8_t *inv_fail);
 
+/* counters of the compiled stage-2 program, the numbers the reference prints (ecm.c:1481-1483) */
+int ecm_b200_stage2_counters(const ecm_b200_ctx *ctx, uint64_t *ptadds, uint64_t *numinv, uint64_t *paired, uint64_t *steps);
+
 /* ---- host-side planners (the scalar control flow the reference also runs on the host) ------
  * Stage-1 op stream for B1 (prac(), lucas_cost(), ecm.c:479-884, driven as in ecm.c:1815-1832).
  * Returns the number of stream bytes (also when ops==NULL or cap too small).  counts[0..1] =
@@ -93,6 +96,10 @@ uint64_t ecm_b200_plan_stage1(uint64_t b1, uint8_t *ops, uint64_t cap, uint64_t 
  * returns the number of steps (also when the arrays are NULL / cap too small).                */
 uint32_t ecm_b200_pair(uint64_t lo, uint64_t hi, uint32_t D, uint32_t U, uint32_t *pairmap_v,
                        uint32_t *pairmap_u, uint32_t cap, uint32_t *amin_final, uint32_t *npairs);
+/* Compile the stage-2 program for (B1,B2) without running it; returns its length in instructions.
+ * counts[0..5] = point additions, inversions, pair products, pairmap steps (ecm.c:1481-1483),
+ * final amin, table entries per curve.                                                         */
+uint64_t ecm_b200_plan_stage2(uint64_t b1, uint64_t b2, uint64_t *counts);
 /* Stage-2 geometry chosen for B1 (thread_init, main.c:834-970): D, U, L, R.                    */
 void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R);
 

@@ -83,3 +83,14 @@ def test_pair_counts_match_reference_printout():
     assert (len(v), npairs) == (g["pairmap_steps"], g["s2_paired"])
     D, U, L, R = E.stage2_params(50000)
     assert (D, U, L, R - 3) == (g["D"], g["U"], g["L"], g["R"])
+
+
+@pytest.mark.parametrize("name", ["readme508_b1_5e4", "syn415_b1_1e5", "small96_D1155", "small96_D385", "small96_D210",
+                                  "small96_D120", "small96_D60", "small96_D30", "syn2048_b1_5e3", "syn415_two_ranges"])
+def test_stage2_program_counters_match_reference_printout(name):
+    # "performed %u pt-adds, %u inversions, and %u pair-muls in stage 2" (ecm.c:1482) + pairmap steps
+    g = GOLDEN[name]
+    c = E.plan_stage2(g["b1"], g["b2"])
+    ref = g["counts"]
+    assert {k: c[k] for k in ("s2_ptadds", "s2_numinv", "s2_paired", "pairmap_steps")} == \
+           {k: ref[k] for k in ("s2_ptadds", "s2_numinv", "s2_paired", "pairmap_steps")}
