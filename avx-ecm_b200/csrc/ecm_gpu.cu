@@ -9,6 +9,8 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -90,7 +92,9 @@ struct ecm_b200_ctx {
     Engine *eng = nullptr;
     int nl = 0;                 // engine limbs
     Big n;                      // modulus padded to nl limbs
-    uint32_t max_curves = 0, cap = 0, count = 0, groups = 0;
+    uint32_t max_curves = 0, count = 0, groups = 0;
+    uint32_t T = 0, groups_max = 0;   // curves per group (= threads per stage-1 block), groups allocated
+    Geom G1{0, 0, NSLOT_S1};
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -131,7 +135,7 @@ int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimb
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
         return fail(ECM_B200_ENODEV, "no usable CUDA device (this engine has no CPU fallback)");
     Engine *eng = make_engine(nlimbs);
-    if (!eng) return fail(ECM_B200_EINVAL, "modulus too large: kernels are built for up to 1024 bits (32 limbs)");
+    if (!eng) return fail(ECM_B200_EINVAL, "modulus too large: kernels are built for up to 2048 bits (64 limbs)");
     ecm_b200_ctx *c = new ecm_b200_ctx();
     c->device = device; c->eng = eng; c->nl = eng->nl; c->max_curves = max_curves;
     const int nl = c->nl;
@@ -155,14 +159,32 @@ int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimb
     CUC(eng->prepare());
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&c->ev0)); CUC(cudaEventCreate(&c->ev1));
-    const uint32_t T = eng->threads_s1;
-    c->cap = (max_curves + T - 1) / T * T;
-    c->state_words = (size_t)NSLOT_S1 * nl * c->cap;
+    // Curves per group (= threads per stage-1 block).  Whole multiples of 4 warps keep the four SM
+    // sub-partitions evenly loaded (14 warps = 4,4,3,3 measured 6.9 Tprod/s vs 7.2 with 12).  More
+    // resident warps hide more latency (throughput ~ w/(w+3.6), measured 12..24 warps), but a batch
+    // with fewer groups than SMs leaves SMs idle, while more groups than SMs are time-sliced at full
+    // occupancy by the launch schedule.  Pick the block size that maximises the product.
+    {
+        const uint32_t S = (uint32_t)eng->stride_s1, sms = (uint32_t)c->num_sms;
+        uint32_t bestT = 0; double best = 0;
+        for (uint32_t T = 128; T <= S; T += 128) {
+            const uint32_t gr = (max_curves + T - 1) / T;
+            const double w = T / 32.0;
+            const double score = (double)std::min(gr, sms) / sms * (w / (w + 3.6)) * ((double)max_curves / ((double)gr * T));
+            if (score > best) { best = score; bestT = T; }
+        }
+        if (bestT == 0) bestT = S;                        // kernels whose smem budget allows < 128 threads
+        if (const char *e = getenv("ECM_B200_THREADS")) { uint32_t t = (uint32_t)atoi(e); if (t >= 32 && t <= S && t % 32 == 0) bestT = t; }
+        c->T = bestT;
+        c->groups_max = (max_curves + bestT - 1) / bestT;
+        c->G1 = Geom{bestT, S, NSLOT_S1};
+    }
+    c->state_words = (size_t)c->groups_max * NSLOT_S1 * nl * eng->stride_s1;
     CUC(cudaMalloc(&c->d_state, c->state_words * 4));
     CUC(cudaMemsetAsync(c->d_state, 0, c->state_words * 4, c->stream));
-    c->d_io_words = (size_t)4 * nl * c->cap;
+    c->d_io_words = (size_t)4 * nl * max_curves + 64;
     CUC(cudaMalloc(&c->d_io, c->d_io_words * 4));
-    CUC(cudaMalloc(&c->d_flags, (size_t)c->cap * 2));
+    CUC(cudaMalloc(&c->d_flags, (size_t)max_curves * 2 + 64));
     CUC(cudaMalloc(&c->d_params, eng->params_bytes));
     CUC(cudaMemcpyAsync(c->d_params, eng->params_host(), eng->params_bytes, cudaMemcpyHostToDevice, c->stream));
     eng->set_params_device(c->d_params);
@@ -192,8 +214,7 @@ static int set_count(ecm_b200_ctx *c, uint32_t count)
     if (!c) return fail(ECM_B200_EINVAL, "null context");
     if (count < 1 || count > c->max_curves) return fail(ECM_B200_EINVAL, "count exceeds the context's max_curves");
     c->count = count;
-    const uint32_t T = c->eng->threads_s1;
-    c->groups = (count + T - 1) / T;
+    c->groups = (count + c->T - 1) / c->T;
     c->have_curves = true; c->stage1_done = false; c->p_slot = 0;
     c->total_items = c->next_item = 0; c->launches_total = c->launches_issued = 0;
     return ECM_B200_OK;
@@ -207,7 +228,7 @@ int ecm_b200_load_curves(ecm_b200_ctx *c, uint32_t count, const uint32_t *x, con
     const size_t words = (size_t)c->nl * count;
     CU(cudaMemcpyAsync(c->d_io, x, words * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_io + words, s, words * 4, cudaMemcpyHostToDevice, c->stream));
-    c->eng->load_curves(c->stream, c->d_state, c->cap, count, c->d_io, c->d_io + words);
+    c->eng->load_curves(c->stream, c->d_state, c->G1, c->groups * c->T, count, c->d_io, c->d_io + words);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     return ECM_B200_OK;
@@ -230,7 +251,7 @@ int ecm_b200_build_curves(ecm_b200_ctx *c, uint32_t count, const uint64_t *sigma
     }
     if ((size_t)8 * count > c->d_io_words) return fail(ECM_B200_ENOMEM, "staging buffer too small");
     CU(cudaMemcpyAsync(c->d_io, uv.data(), uv.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    c->eng->build_curves(c->stream, c->d_state, c->cap, count, c->d_io, c->d_flags);
+    c->eng->build_curves(c->stream, c->d_state, c->G1, c->groups * c->T, count, c->d_io, c->d_flags);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     return ECM_B200_OK;
@@ -283,7 +304,7 @@ int ecm_b200_stage1_step(ecm_b200_ctx *c, uint32_t max_launches, int *done)
     uint32_t n = 0;
     while (c->next_item < c->total_items && n < max_launches) {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(per, c->total_items - c->next_item);
-        c->eng->stage1(c->stream, blocks, c->d_state, c->cap, c->d_ops, c->plan.ops.size(), c->chunk_len, c->groups, c->next_item);
+        c->eng->stage1(c->stream, blocks, c->T, c->d_state, c->d_ops, c->plan.ops.size(), c->chunk_len, c->groups, c->next_item);
         c->next_item += blocks; c->launches_issued++; c->last_launches++; n++;
     }
     CU(cudaGetLastError());
@@ -384,7 +405,7 @@ int ecm_b200_read_stage1(ecm_b200_ctx *c, uint32_t *x, uint32_t *z, uint8_t *fac
     const size_t words = (size_t)c->nl * c->count;
     uint32_t *dx = c->d_io, *dz = c->d_io + words, *dg = c->d_io + 2 * words;
     const bool want_flag = factor_flag || gcd_out;
-    c->eng->read_point(c->stream, c->d_state, c->cap, c->count, 2 * c->p_slot, 2 * c->p_slot + 1, x ? dx : nullptr, dz,
+    c->eng->read_point(c->stream, c->d_state, c->G1, c->count, 2 * c->p_slot, 2 * c->p_slot + 1, x ? dx : nullptr, dz,
                        want_flag ? c->d_flags : nullptr, gcd_out ? dg : nullptr);
     CU(cudaGetLastError());
     if (x) CU(cudaMemcpyAsync(x, dx, words * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -452,7 +473,7 @@ int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
     for (uint32_t first = 0; first < c->count; first += cap2) {
         const uint32_t n = std::min<uint32_t>(cap2, c->count - first);
         const uint32_t groups = (n + T - 1) / T;
-        c->eng->s2_setup(c->stream, c->d_state, c->cap, 2 * c->p_slot, 2 * c->p_slot + 1, SP, first, c->count, state2, cap2, tab,
+        c->eng->s2_setup(c->stream, c->d_state, c->G1, 2 * c->p_slot, 2 * c->p_slot + 1, SP, first, c->count, state2, cap2, tab,
                          pg.lay.qx, pg.lay.qz, wfail);
         CUS(cudaMemcpyAsync(d_code, pg.init.data(), pg.init.size() * 8, cudaMemcpyHostToDevice, c->stream));
         int rc = run_program(c, d_code, pg.init.size(), state2, cap2, tab, groups, wfail);
@@ -484,7 +505,7 @@ int ecm_b200_read_stage2(ecm_b200_ctx *c, uint32_t *acc, uint8_t *factor_flag, u
     uint32_t *da = c->d_io, *dg = c->d_io + words;
     const bool want_flag = factor_flag || gcd_out;
     // d_acc is laid out like a one-slot state with cap = count
-    c->eng->read_point(c->stream, c->d_acc, c->count, c->count, 0, 0, nullptr, da, want_flag ? c->d_flags : nullptr,
+    c->eng->read_point(c->stream, c->d_acc, Geom{c->count, c->count, 1}, c->count, 0, 0, nullptr, da, want_flag ? c->d_flags : nullptr,
                        gcd_out ? dg : nullptr);
     CU(cudaGetLastError());
     if (acc) CU(cudaMemcpyAsync(acc, da, words * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -509,7 +530,7 @@ int ecm_b200_stage2_counters(const ecm_b200_ctx *c, uint64_t *ptadds, uint64_t *
 int ecm_b200_fieldop(ecm_b200_ctx *c, int op, uint32_t count, const uint32_t *a, const uint32_t *b, uint32_t *r, int repeat)
 {
     if (!c || !a || !b || !r || op < 0 || op > 3 || repeat < 1) return fail(ECM_B200_EINVAL, "bad argument");
-    if (count > c->cap) return fail(ECM_B200_EINVAL, "count exceeds the context's capacity");
+    if (count > c->max_curves) return fail(ECM_B200_EINVAL, "count exceeds the context's capacity");
     CU(cudaSetDevice(c->device));
     const size_t words = (size_t)c->nl * count;
     CU(cudaMemcpyAsync(c->d_io, a, words * 4, cudaMemcpyHostToDevice, c->stream));

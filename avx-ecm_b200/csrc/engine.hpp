@@ -4,30 +4,31 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <vector>
+#include "geom.hpp"
 
 namespace ecmb200 {
 
 typedef std::vector<uint32_t> Big;
 
 struct Engine {
-    int nl = 0, threads_s1 = 0, smem_s1 = 0;
+    int nl = 0, stride_s1 = 0, smem_s1 = 0;      // stride_s1 = max threads per stage-1 block = lane stride of the state
     size_t params_bytes = 0;
     virtual ~Engine() {}
     virtual void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, uint32_t m0inv) = 0;
     virtual const void *params_host() const = 0;        // ModParams<NL> image to copy to the device
     virtual void set_params_device(const void *d) = 0;  // device copy for the out-of-line kernels
     virtual cudaError_t prepare() = 0;
-    virtual void stage1(cudaStream_t st, uint32_t blocks, uint32_t *state, uint32_t cap, const uint8_t *ops, uint64_t nops,
+    virtual void stage1(cudaStream_t st, uint32_t blocks, uint32_t threads, uint32_t *state, const uint8_t *ops, uint64_t nops,
                         uint32_t chunk_len, uint32_t groups, uint64_t item0) = 0;
-    virtual void load_curves(cudaStream_t st, uint32_t *state, uint32_t cap, uint32_t count, const uint32_t *x, const uint32_t *s) = 0;
-    virtual void build_curves(cudaStream_t st, uint32_t *state, uint32_t cap, uint32_t count, const uint32_t *uv, uint8_t *ok) = 0;
-    virtual void read_point(cudaStream_t st, const uint32_t *state, uint32_t cap, uint32_t count, uint32_t xs, uint32_t zs,
+    virtual void load_curves(cudaStream_t st, uint32_t *state, Geom G, uint32_t lanes, uint32_t count, const uint32_t *x, const uint32_t *s) = 0;
+    virtual void build_curves(cudaStream_t st, uint32_t *state, Geom G, uint32_t lanes, uint32_t count, const uint32_t *uv, uint8_t *ok) = 0;
+    virtual void read_point(cudaStream_t st, const uint32_t *state, Geom G, uint32_t count, uint32_t xs, uint32_t zs,
                             uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g) = 0;
     // stage 2
     int threads_s2 = 0, smem_s2 = 0, nslot_s2 = 0;
     virtual void vm2(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, uint32_t *tab, const uint64_t *code,
                      uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0, uint8_t *inv_fail) = 0;
-    virtual void s2_setup(cudaStream_t st, const uint32_t *state1, uint32_t cap1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
+    virtual void s2_setup(cudaStream_t st, const uint32_t *state1, Geom G1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
                           uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab, uint32_t e_qx,
                           uint32_t e_qz, uint8_t *inv_fail) = 0;
     virtual void s2_collect(cudaStream_t st, const uint32_t *state2, uint32_t cap2, const uint8_t *inv_fail, uint32_t first,

@@ -14,7 +14,7 @@ struct EngineT : Engine {
     const ModParams<NL> *Pg = nullptr;
     EngineT()
     {
-        nl = NL; threads_s1 = BlockCfg<NL, NSLOT_S1>::THREADS; smem_s1 = BlockCfg<NL, NSLOT_S1>::smem;
+        nl = NL; stride_s1 = S1Cfg<NL>::STRIDE; smem_s1 = S1Cfg<NL>::smem;
         params_bytes = sizeof(ModParams<NL>);
         threads_s2 = BlockCfg<NL, NSLOT_S2>::THREADS; smem_s2 = BlockCfg<NL, NSLOT_S2>::smem; nslot_s2 = NSLOT_S2;
     }
@@ -37,11 +37,11 @@ struct EngineT : Engine {
         k_vm2<NL><<<blocks, threads_s2, smem_s2, st>>>(P, Pg, state2, cap, tab, code, ncode, chunk_len, groups, item0, inv_fail);
         count_launch();
     }
-    void s2_setup(cudaStream_t st, const uint32_t *state1, uint32_t cap1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
+    void s2_setup(cudaStream_t st, const uint32_t *state1, Geom G1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
                   uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab, uint32_t e_qx, uint32_t e_qz,
                   uint8_t *inv_fail) override
     {
-        k_s2_setup<NL><<<(cap2 + 127) / 128, 128, 0, st>>>(state1, cap1, xslot, zslot, spslot, first, count, state2, cap2, tab, e_qx, e_qz, inv_fail);
+        k_s2_setup<NL><<<(cap2 + 127) / 128, 128, 0, st>>>(state1, dg(G1), xslot, zslot, spslot, first, count, state2, cap2, tab, e_qx, e_qz, inv_fail);
         count_launch();
     }
     void s2_collect(cudaStream_t st, const uint32_t *state2, uint32_t cap2, const uint8_t *inv_fail, uint32_t first, uint32_t n,
@@ -50,26 +50,27 @@ struct EngineT : Engine {
         k_s2_collect<NL><<<(n + 127) / 128, 128, 0, st>>>(state2, cap2, inv_fail, first, n, count, acc_out, fail_out);
         count_launch();
     }
-    void stage1(cudaStream_t st, uint32_t blocks, uint32_t *state, uint32_t cap, const uint8_t *ops, uint64_t nops,
+    static Geom dg(const Geom &G) { return G; }
+    void stage1(cudaStream_t st, uint32_t blocks, uint32_t threads, uint32_t *state, const uint8_t *ops, uint64_t nops,
                 uint32_t chunk_len, uint32_t groups, uint64_t item0) override
     {
-        k_stage1<NL><<<blocks, threads_s1, smem_s1, st>>>(P, state, cap, ops, nops, chunk_len, groups, item0);
+        k_stage1<NL><<<blocks, threads, smem_s1, st>>>(P, state, ops, nops, chunk_len, groups, item0);
         count_launch();
     }
-    void load_curves(cudaStream_t st, uint32_t *state, uint32_t cap, uint32_t count, const uint32_t *x, const uint32_t *s) override
+    void load_curves(cudaStream_t st, uint32_t *state, Geom G, uint32_t lanes, uint32_t count, const uint32_t *x, const uint32_t *s) override
     {
-        k_load_curves<NL><<<(cap + 127) / 128, 128, 0, st>>>(Pg, state, cap, count, x, s);
+        k_load_curves<NL><<<(lanes + 127) / 128, 128, 0, st>>>(Pg, state, dg(G), lanes, count, x, s);
         count_launch();
     }
-    void build_curves(cudaStream_t st, uint32_t *state, uint32_t cap, uint32_t count, const uint32_t *uv, uint8_t *ok) override
+    void build_curves(cudaStream_t st, uint32_t *state, Geom G, uint32_t lanes, uint32_t count, const uint32_t *uv, uint8_t *ok) override
     {
-        k_build_curves<NL><<<(cap + 63) / 64, 64, 0, st>>>(Pg, state, cap, count, uv, ok);
+        k_build_curves<NL><<<(lanes + 63) / 64, 64, 0, st>>>(Pg, state, dg(G), lanes, count, uv, ok);
         count_launch();
     }
-    void read_point(cudaStream_t st, const uint32_t *state, uint32_t cap, uint32_t count, uint32_t xs, uint32_t zs,
+    void read_point(cudaStream_t st, const uint32_t *state, Geom G, uint32_t count, uint32_t xs, uint32_t zs,
                     uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g) override
     {
-        k_read_point<NL><<<(count + 63) / 64, 64, 0, st>>>(Pg, state, cap, count, xs, zs, x, z, flag, g);
+        k_read_point<NL><<<(count + 63) / 64, 64, 0, st>>>(Pg, state, dg(G), count, xs, zs, x, z, flag, g);
         count_launch();
     }
     void fieldop(cudaStream_t st, int op, uint32_t count, const uint32_t *a, const uint32_t *b, uint32_t *r, int repeat) override

@@ -1,14 +1,18 @@
 // kernels.cuh -- __global__ entry points, templated on the limb count NL.
-// Device state of a batch: state[(slot*NL + limb) * cap + curve]  (limb-major, curve fastest:
-// a warp's 32 curves read 128 contiguous bytes per limb -- the coalesced analogue of the
-// reference's bignum.data[lane + word*VECLEN], vec_common.c:32-54).
+// Device state of a batch: curves are cut into groups of T (= threads per block); group g owns
+//   state[((g*NSLOT + slot)*NL + limb)*STRIDE + lane]        (Geom below)
+// limb-major with the curve (lane) fastest: a warp's 32 curves read 128 contiguous bytes per limb --
+// the coalesced analogue of the reference's bignum.data[lane + word*VECLEN], vec_common.c:32-54.
 #pragma once
+#include "geom.hpp"
 #include "vm.cuh"
 #include "modinv.cuh"
 
 namespace ecmb200 {
 
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int NSMEM_S1 = 5;      // stage-1 slots kept in shared memory (s1,d1,s2,d2,sp); the 8 point slots stay in global
+
 template <int NL, int NSLOT>
 struct BlockCfg {
     static constexpr int per_thread = NSLOT * NL * 4;
@@ -30,23 +34,34 @@ __device__ __forceinline__ void gstore(uint32_t *state, uint32_t cap, uint32_t s
     for (int k = 0; k < NL; k++) state[((size_t)slot * NL + k) * cap + curve] = r[k];
 }
 
-// ---- stage 1: interpret macro-ops [chunk*chunk_len, ...) for one group of THREADS curves ------
+// ---- stage 1: interpret macro-ops [chunk*chunk_len, ...) for one group of blockDim.x curves ------
 template <int NL>
-__global__ void __launch_bounds__(BlockCfg<NL, NSLOT_S1>::THREADS, 1)
-k_stage1(const ModParams<NL> P, uint32_t *__restrict__ state, uint32_t cap, const uint8_t *__restrict__ ops,
+struct S1Cfg {
+    static constexpr int per_thread = NSMEM_S1 * NL * 4;
+    static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
+    static constexpr int STRIDE = fit > 768 ? 768 : fit;          // max threads per block = lane stride
+    static constexpr int smem = per_thread * STRIDE;
+};
+
+template <int NL>
+__global__ void __launch_bounds__(S1Cfg<NL>::STRIDE, 1)
+k_stage1(const ModParams<NL> P, uint32_t *__restrict__ state, const uint8_t *__restrict__ ops,
          uint64_t nops, uint32_t chunk_len, uint32_t groups, uint64_t item0)
 {
-    constexpr int THREADS = BlockCfg<NL, NSLOT_S1>::THREADS;
+    constexpr int STRIDE = S1Cfg<NL>::STRIDE;
     extern __shared__ uint32_t smem[];
     const uint64_t item = item0 + blockIdx.x;
     const uint32_t g = (uint32_t)(item % groups);
     const uint64_t chunk = item / groups;
-    const uint32_t curve = g * THREADS + threadIdx.x;
-    Slots<NL, THREADS> S{smem + threadIdx.x};
+    HybridSlots<NL, STRIDE> S{state + (size_t)g * (NSLOT_S1 * NL * STRIDE) + threadIdx.x, smem + threadIdx.x};
 
     uint32_t r[NL];
 #pragma unroll 1
-    for (uint32_t s = 0; s < NSLOT_S1; s++) { gload<NL>(r, state, cap, s, curve); S.store(s, r); }
+    for (uint32_t s = 8; s < NSLOT_S1; s++) {          // scratch slots: global image -> shared
+#pragma unroll
+        for (int k = 0; k < NL; k++) r[k] = S.gl[(s * NL + k) * STRIDE];
+        S.store(s, r);
+    }
 
     uint64_t i = chunk * chunk_len;
     const uint64_t end = (i + chunk_len < nops) ? i + chunk_len : nops;
@@ -63,11 +78,15 @@ k_stage1(const ModParams<NL> P, uint32_t *__restrict__ state, uint32_t cap, cons
         for (int k = 0;; k++) {
             const uint32_t u = c_prog_s1[type][k];
             if ((u & 15u) == U_END) break;
-            exec_uop<NL, THREADS>(S, u, permbits, P);
+            exec_uop<NL>(S, u, permbits, P);
         }
     }
 #pragma unroll 1
-    for (uint32_t s = 0; s < NSLOT_S1; s++) { S.load(r, s); gstore<NL>(state, cap, s, curve, r); }
+    for (uint32_t s = 8; s < NSLOT_S1; s++) {
+        S.load(r, s);
+#pragma unroll
+        for (int k = 0; k < NL; k++) S.gl[(s * NL + k) * STRIDE] = r[k];
+    }
 }
 
 // ---- out-of-line helpers for the set-up / read-out kernels (speed is irrelevant there; keeping
@@ -108,11 +127,11 @@ __device__ __noinline__ bool nm_inverse(uint32_t *inv, uint32_t *g, const uint32
 // ---- curve set-up -----------------------------------------------------------------------------
 // host-built curves: plain x = X/Z and s = (A+2)/4  ->  Montgomery form, Z = 1; P sits in point slot 0
 template <int NL>
-__global__ void k_load_curves(const ModParams<NL> *Pg, uint32_t *state, uint32_t cap, uint32_t count,
+__global__ void k_load_curves(const ModParams<NL> *Pg, uint32_t *state, Geom G, uint32_t lanes, uint32_t count,
                               const uint32_t *x, const uint32_t *s)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cap) return;
+    if (c >= lanes) return;
     const uint32_t src = c < count ? c : count - 1;          // padding lanes replicate the last curve
     uint32_t a[NL], t[NL];
 #pragma unroll 1
@@ -120,9 +139,9 @@ __global__ void k_load_curves(const ModParams<NL> *Pg, uint32_t *state, uint32_t
         const uint32_t *in = which ? s : x;
         for (int k = 0; k < NL; k++) a[k] = in[(size_t)k * count + src];
         nm_mul<NL>(t, a, Pg->r2, Pg);
-        for (int k = 0; k < NL; k++) state[((size_t)(which ? SP : 0) * NL + k) * cap + c] = t[k];
+        for (int k = 0; k < NL; k++) state[G.idx(c, which ? SP : 0, k, NL)] = t[k];
     }
-    for (int k = 0; k < NL; k++) state[((size_t)1 * NL + k) * cap + c] = Pg->one[k];
+    for (int k = 0; k < NL; k++) state[G.idx(c, 1, k, NL)] = Pg->one[k];
 }
 
 // Suyama "param 0" curve from u = sigma^2-5, v = 4*sigma (both already reduced mod N, 4 limbs each,
@@ -131,11 +150,11 @@ __global__ void k_load_curves(const ModParams<NL> *Pg, uint32_t *state, uint32_t
 // One shared inversion of (v^3 * 16u^3v) replaces the reference's two mpz_invert calls; the
 // quotients are the same residues.  ok[c] = 0 when that product is not invertible mod N.
 template <int NL>
-__global__ void k_build_curves(const ModParams<NL> *Pg, uint32_t *state, uint32_t cap, uint32_t count,
+__global__ void k_build_curves(const ModParams<NL> *Pg, uint32_t *state, Geom G, uint32_t lanes, uint32_t count,
                                const uint32_t *uv, uint8_t *ok)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cap) return;
+    if (c >= lanes) return;
     const uint32_t src = c < count ? c : count - 1;
     uint32_t u[NL], v[NL], t1[NL], t2[NL], u3[NL], v3[NL], num[NL], den[NL], inv[NL], g[NL];
     for (int k = 0; k < NL; k++) {
@@ -160,9 +179,9 @@ __global__ void k_build_curves(const ModParams<NL> *Pg, uint32_t *state, uint32_
     nm_mul<NL>(t1, t1, u3, Pg);                                   // X = u^3/v^3
     nm_mul<NL>(t2, t2, num, Pg);                                  // s
     for (int k = 0; k < NL; k++) {
-        state[((size_t)0 * NL + k) * cap + c] = t1[k];
-        state[((size_t)1 * NL + k) * cap + c] = Pg->one[k];
-        state[((size_t)SP * NL + k) * cap + c] = t2[k];
+        state[G.idx(c, 0, k, NL)] = t1[k];
+        state[G.idx(c, 1, k, NL)] = Pg->one[k];
+        state[G.idx(c, SP, k, NL)] = t2[k];
     }
     if (c < count) ok[c] = good ? 1 : 0;
 }
@@ -171,7 +190,7 @@ __global__ void k_build_curves(const ModParams<NL> *Pg, uint32_t *state, uint32_
 // X*1, Z*1 leave Montgomery form (ecm.c:1327-1331); gcd(Z,N) is the stage-1 factor test
 // (ecm.c:1335-1342, check_factor ecm.c:2542-2557: 1 < g < N).
 template <int NL>
-__global__ void k_read_point(const ModParams<NL> *Pg, const uint32_t *state, uint32_t cap, uint32_t count,
+__global__ void k_read_point(const ModParams<NL> *Pg, const uint32_t *state, Geom G, uint32_t count,
                              uint32_t xslot, uint32_t zslot, uint32_t *x_out, uint32_t *z_out,
                              uint8_t *flag, uint32_t *g_out)
 {
@@ -183,7 +202,7 @@ __global__ void k_read_point(const ModParams<NL> *Pg, const uint32_t *state, uin
     for (int which = 0; which < 2; which++) {
         uint32_t *out = which ? z_out : x_out;
         if (!out && !(which && flag)) continue;
-        for (int k = 0; k < NL; k++) a[k] = state[((size_t)(which ? zslot : xslot) * NL + k) * cap + c];
+        for (int k = 0; k < NL; k++) a[k] = state[G.idx(c, which ? zslot : xslot, k, NL)];
         if (out) {
             nm_mul<NL>(r, a, one, Pg);
             for (int k = 0; k < NL; k++) out[(size_t)k * count + c] = r[k];
@@ -330,7 +349,7 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
 // the wave's table / slot file.  Wave curve c is batch curve first + c (clamped: padding lanes repeat
 // the last curve).
 template <int NL>
-__global__ void k_s2_setup(const uint32_t *state1, uint32_t cap1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
+__global__ void k_s2_setup(const uint32_t *state1, Geom G1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
                            uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab,
                            uint32_t e_qx, uint32_t e_qz, uint8_t *inv_fail)
 {
@@ -338,10 +357,10 @@ __global__ void k_s2_setup(const uint32_t *state1, uint32_t cap1, uint32_t xslot
     if (c >= cap2) return;
     uint32_t src = first + c; if (src >= count) src = count - 1;
     for (int k = 0; k < NL; k++) {
-        tab[((size_t)e_qx * NL + k) * cap2 + c] = state1[((size_t)xslot * NL + k) * cap1 + src];
-        tab[((size_t)e_qz * NL + k) * cap2 + c] = state1[((size_t)zslot * NL + k) * cap1 + src];
+        tab[((size_t)e_qx * NL + k) * cap2 + c] = state1[G1.idx(src, xslot, k, NL)];
+        tab[((size_t)e_qz * NL + k) * cap2 + c] = state1[G1.idx(src, zslot, k, NL)];
         for (uint32_t s = 0; s < NSLOT_S2; s++)
-            state2[((size_t)s * NL + k) * cap2 + c] = (s == V2_SP) ? state1[((size_t)spslot * NL + k) * cap1 + src] : 0;
+            state2[((size_t)s * NL + k) * cap2 + c] = (s == V2_SP) ? state1[G1.idx(src, spslot, k, NL)] : 0;
     }
     inv_fail[c] = 0;
 }

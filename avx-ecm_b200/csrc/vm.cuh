@@ -92,9 +92,45 @@ __device__ __forceinline__ uint32_t resolve(uint32_t sym, uint32_t permbits)
     return (sym < 8) ? (2u * ((permbits >> (2u * (sym >> 1))) & 3u) + (sym & 1u)) : sym;
 }
 
+// Hybrid slot file of the stage-1 machine: the four points (slots 0..7) stay in the batch state
+// in global memory -- L2-resident, [group][slot][limb][STRIDE] so that limb offsets are immediates
+// and a warp reads 128 contiguous bytes -- while the five hot scratch slots (s1,d1,s2,d2,sp) live in
+// shared memory.  A multiply takes thousands of cycles, so the L2 latency of the point reads is
+// hidden by the other resident warps, and the small shared footprint (5 slots) is what lets 14-16
+// warps share an SM instead of 10.
+template <int NL, int STRIDE>
+struct HybridSlots {
+    uint32_t *gl;     // state of this block's group + threadIdx.x
+    uint32_t *sm;     // smem + threadIdx.x
+    __device__ __forceinline__ void load(uint32_t (&r)[NL], uint32_t slot) const
+    {
+        if (slot < 8) {
+            const uint32_t *p = gl + slot * (NL * STRIDE);
+#pragma unroll
+            for (int k = 0; k < NL; k++) r[k] = p[k * STRIDE];
+        } else {
+            const uint32_t *p = sm + (slot - 8) * (NL * STRIDE);
+#pragma unroll
+            for (int k = 0; k < NL; k++) r[k] = p[k * STRIDE];
+        }
+    }
+    __device__ __forceinline__ void store(uint32_t slot, const uint32_t (&r)[NL]) const
+    {
+        if (slot < 8) {
+            uint32_t *p = gl + slot * (NL * STRIDE);
+#pragma unroll
+            for (int k = 0; k < NL; k++) p[k * STRIDE] = r[k];
+        } else {
+            uint32_t *p = sm + (slot - 8) * (NL * STRIDE);
+#pragma unroll
+            for (int k = 0; k < NL; k++) p[k * STRIDE] = r[k];
+        }
+    }
+};
+
 // Execute one micro-op on the slot file.
-template <int NL, int THREADS>
-__device__ __forceinline__ void exec_uop(const Slots<NL, THREADS> &S, uint32_t u, uint32_t permbits,
+template <int NL, class SlotsT>
+__device__ __forceinline__ void exec_uop(const SlotsT &S, uint32_t u, uint32_t permbits,
                                          const ModParams<NL> &P)
 {
     const uint32_t op = u & 15u;

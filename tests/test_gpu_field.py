@@ -12,7 +12,7 @@ def moduli():
     c = composites()
     return {
         "small96": c["small96"], "t35_297b": c["t35"], "syn415": c["syn415"], "readme508": c["readme508"],
-        "syn1024_fullwidth": c["syn1024"], "allones_416": (1 << 416) - 1 - 2 * 0,   # odd, every limb 0xffffffff
+        "syn1024_fullwidth": c["syn1024"], "syn2048_fullwidth": c["syn2048"], "odd_700b": (1 << 700) - 1 - (1 << 350), "allones_416": (1 << 416) - 1 - 2 * 0,   # odd, every limb 0xffffffff
         "tiny_3limb": (1 << 65) + 13,
     }
 
@@ -49,4 +49,4 @@ def test_rejects_even_modulus_and_oversize():
     with pytest.raises(E.EcmError):
         E.EcmContext(1 << 200, 8)
     with pytest.raises(E.EcmError):
-        E.EcmContext((1 << 2047) + 1, 8)      # larger than the widest compiled kernel (for now)
+        E.EcmContext((1 << 2100) + 1, 8)      # larger than the widest compiled kernel (64 limbs)

@@ -7,7 +7,7 @@ import avx_ecm_b200 as E
 
 pytestmark = pytest.mark.gpu
 
-MAXBITS = 1024
+MAXBITS = 2048
 
 
 def usable(g):

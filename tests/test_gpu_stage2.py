@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def usable(g):
-    return int(g["n"]).bit_length() <= 1024 and g["b2"] > g["b1"]
+    return int(g["n"]).bit_length() <= 2048 and g["b2"] > g["b1"]
 
 
 @pytest.mark.parametrize("name", sorted(k for k, g in GOLDEN.items() if usable(g)))
