@@ -1,0 +1,179 @@
+// avx-ecm-b200 -- command-line driver with avx-ecm's argument contract
+//     avx-ecm-b200 $input $numcurves $B1 [$gpus] [$B2] [$sigma]
+// (main.c:380-384; the 4th argument, the reference's thread count, is the number of GPUs here: one
+// host thread per GPU, each with its own engine context and a disjoint sigma range).  Writes the
+// reference's output files in its formats: save_b1.txt (GMP-ECM resume lines, ecm.c:1372-1380)
+// and ecm_results.txt (ecm.c:1362-1366, 1517-1520).  All arithmetic on the hot path runs on the
+// GPUs through include/ecm_b200.h; GMP is used for the expression, file output and PRP labels.
+#include <inttypes.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include <unistd.h>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../include/ecm_b200.h"
+#include "calc.hpp"
+
+static double now()
+{
+    struct timeval t; gettimeofday(&t, NULL);
+    return t.tv_sec + t.tv_usec * 1e-6;
+}
+
+// Knuth's MMIX LCG, the generator the reference draws random sigmas from (main.c:993-998)
+static uint64_t lcg_next(uint64_t *s) { *s = 6364136223846793005ULL * *s + 1442695040888963407ULL; return *s; }
+
+struct Shard {
+    int gpu = 0;
+    uint32_t first = 0, count = 0;
+    std::vector<uint64_t> sigma;
+    std::vector<uint32_t> X, Z, G1, G2;
+    std::vector<uint8_t> f1, f2;
+    int limbs = 0;
+    double t_build = 0, t_s1 = 0, t_s2 = 0;
+    std::string error;
+};
+
+static void run_shard(Shard *s, const std::vector<uint32_t> *n32, uint64_t b1, uint64_t b2, bool do2)
+{
+    ecm_b200_ctx *ctx = NULL;
+    if (ecm_b200_create(&ctx, s->gpu, n32->data(), (int)n32->size(), s->count)) { s->error = ecm_b200_last_error(); return; }
+    const int L = s->limbs = ecm_b200_limbs(ctx);
+    const size_t words = (size_t)L * s->count;
+    s->X.resize(words); s->Z.resize(words); s->G1.resize(words); s->f1.resize(s->count);
+    double t0 = now();
+    int rc = ecm_b200_build_curves(ctx, s->count, s->sigma.data());
+    s->t_build = now() - t0; t0 = now();
+    if (!rc) rc = ecm_b200_stage1(ctx, b1);
+    if (!rc) rc = ecm_b200_read_stage1(ctx, s->X.data(), s->Z.data(), s->f1.data(), s->G1.data());
+    s->t_s1 = now() - t0; t0 = now();
+    if (!rc && do2) {
+        s->G2.resize(words); s->f2.resize(s->count);
+        rc = ecm_b200_stage2(ctx, b1, b2);
+        if (!rc) rc = ecm_b200_read_stage2(ctx, NULL, s->f2.data(), s->G2.data(), NULL);
+        s->t_s2 = now() - t0;
+    }
+    if (rc) s->error = ecm_b200_last_error();
+    ecm_b200_destroy(ctx);
+}
+
+static void limbs_to_mpz(mpz_t out, const std::vector<uint32_t> &buf, int L, uint32_t count, uint32_t i)
+{
+    std::vector<uint32_t> t(L);
+    for (int k = 0; k < L; k++) t[k] = buf[(size_t)k * count + i];
+    mpz_import(out, L, -1, 4, 0, 0, t.data());
+}
+
+static void report(FILE *res, mpz_t f, int stage, uint64_t bound, uint32_t curve, uint64_t sigma)
+{
+    char ftype[32];
+    snprintf(ftype, sizeof ftype, "%s%d", mpz_probab_prime_p(f, 3) ? "PRP" : "C", (int)mpz_sizeinbase(f, 10));
+    gmp_printf("\nfound %s factor %Zd in stage %d (B%d = %" PRIu64 "): thread %d, vec %d, sigma %" PRIu64 "\n",
+               ftype, f, stage, stage, bound, 0, (int)(curve % 8), sigma);
+    if (res)
+        gmp_fprintf(res, "\nfound %s factor %Zd in stage %d (B%d = %" PRIu64 "): curve %d, thread %d, vec %d, sigma %" PRIu64 "\n",
+                    ftype, f, stage, stage, bound, (int)curve, 0, (int)(curve % 8), sigma);
+    fflush(stdout);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc == 3 && strcmp(argv[1], "--eval") == 0) {          // expression evaluator only
+        mpz_t v; mpz_init(v);
+        std::string e = calc_eval(argv[2], v);
+        if (!e.empty()) { printf("error: %s\n", e.c_str()); return 1; }
+        gmp_printf("%Zd\n", v);
+        return 0;
+    }
+    if (argc < 4) {
+        printf("usage: avx-ecm-b200 $input $numcurves $B1 [$gpus] [$B2] [$sigma]\n");
+        return 1;
+    }
+    const double t_start = now();
+    printf("starting process %d\n", (int)getpid());
+    mpz_t N, x, z, f;
+    mpz_init(N); mpz_init(x); mpz_init(z); mpz_init(f);
+    std::string err = calc_eval(argv[1], N);
+    if (!err.empty()) { printf("could not evaluate input expression: %s\n", err.c_str()); return 1; }
+    if (mpz_cmp_ui(N, 3) < 0 || !mpz_odd_p(N)) { printf("input must be an odd integer > 2\n"); return 1; }
+
+    uint32_t numcurves = (uint32_t)strtoul(argv[2], NULL, 10);
+    const uint64_t b1 = strtoull(argv[3], NULL, 10);
+    uint64_t b2 = 100ULL * b1;                                  // main.c:462
+    int gpus = (argc >= 5) ? atoi(argv[4]) : 1;
+    if (gpus < 1) gpus = 1;
+    bool do2 = true;
+    if (argc >= 6) { b2 = strtoull(argv[5], NULL, 10); if (b2 <= b1) { do2 = false; b2 = b1; } }   // main.c:543-552
+    uint64_t sigma0 = (argc >= 7) ? strtoull(argv[6], NULL, 10) : 0;
+    if (numcurves < (uint32_t)gpus) numcurves = gpus;
+
+    gmp_printf("commencing parallel ecm on %Zd\n", N);
+    const int bits = (int)mpz_sizeinbase(N, 2);
+    printf("ECM has been configured with 32-bit limbs on B200 (%d limbs), GMP_LIMB_BITS = %d\n", (bits + 31) / 32, GMP_LIMB_BITS);
+    if (sigma0) printf("starting with sigma = %" PRIu64 "\n", sigma0);
+    printf("Input has %d bits, using %d GPU(s) (%u curves/GPU)\n", bits, gpus, (numcurves + gpus - 1) / gpus);
+
+    std::vector<uint32_t> n32((bits + 31) / 32, 0);
+    size_t cnt = 0;
+    mpz_export(n32.data(), &cnt, -1, 4, 0, 0, N);
+
+    // contiguous sigma slices, one per GPU; random sigmas when none was given (ecm.c:1564-1570)
+    std::vector<Shard> shards(gpus);
+    uint64_t lcg = (uint64_t)(t_start * 1e6) ^ ((uint64_t)getpid() << 32);
+    uint32_t first = 0;
+    for (int g = 0; g < gpus; g++) {
+        Shard &s = shards[g];
+        s.gpu = g; s.first = first;
+        s.count = numcurves / gpus + ((uint32_t)g < numcurves % gpus ? 1 : 0);
+        first += s.count;
+        s.sigma.resize(s.count);
+        for (uint32_t i = 0; i < s.count; i++) {
+            if (sigma0) s.sigma[i] = sigma0 + s.first + i;
+            else { uint64_t v; do { v = lcg_next(&lcg); } while (v < 6); s.sigma[i] = v; }
+        }
+    }
+    printf("\nCommencing curves 0-%u of %u\n", numcurves - 1, numcurves);
+    std::vector<std::thread> th;
+    for (int g = 0; g < gpus; g++) th.emplace_back(run_shard, &shards[g], &n32, b1, b2, do2);
+    for (auto &t : th) t.join();
+    double ts1 = 0, ts2 = 0, tb = 0;
+    for (auto &s : shards) {
+        if (!s.error.empty()) { printf("GPU %d: %s\n", s.gpu, s.error.c_str()); return 1; }
+        ts1 = std::max(ts1, s.t_s1); ts2 = std::max(ts2, s.t_s2); tb = std::max(tb, s.t_build);
+    }
+    printf("Building curves took %1.4f seconds.\n", tb);
+    printf("Stage 1 took %1.4f seconds\n", ts1);
+
+    // save_b1.txt, in sigma order = batch/thread/lane order of the reference with threads=1
+    int found = 0;
+    FILE *save = fopen("save_b1.txt", "a");
+    FILE *res = fopen("ecm_results.txt", "a");
+    if (!save) printf("could not open save_b1.txt for appending, Stage 1 data will not be saved\n");
+    for (auto &s : shards) {
+        for (uint32_t i = 0; i < s.count; i++) {
+            limbs_to_mpz(x, s.X, s.limbs, s.count, i);
+            limbs_to_mpz(z, s.Z, s.limbs, s.count, i);
+            if (mpz_sgn(z) == 0) printf("something failed: curve %u has zero result\n", s.first + i);
+            if (s.f1[i]) { limbs_to_mpz(f, s.G1, s.limbs, s.count, i); report(res, f, 1, b1, s.first + i, s.sigma[i]); found = 1; }
+            if (save) {
+                fprintf(save, "METHOD=ECM; SIGMA=%" PRIu64 "; B1=%" PRIu64 "; ", s.sigma[i], b1);
+                gmp_fprintf(save, "N=0x%Zx; X=0x%Zx; Z=0x%Zx; PROGRAM=AVX-ECM;\n", N, x, z);
+            }
+        }
+    }
+    if (save) fclose(save);
+    if (do2) {
+        printf("Stage 2 took %1.4f seconds\n", ts2);
+        for (auto &s : shards)
+            for (uint32_t i = 0; i < s.count; i++)
+                if (s.f2[i]) { limbs_to_mpz(f, s.G2, s.limbs, s.count, i); report(res, f, 2, b2, s.first + i, s.sigma[i]); found = 1; }
+    }
+    if (res) fclose(res);
+    printf("Process took %1.4f seconds.\n", now() - t_start);
+    (void)found;
+    return 0;
+}

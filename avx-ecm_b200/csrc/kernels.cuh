@@ -39,7 +39,9 @@ template <int NL>
 struct S1Cfg {
     static constexpr int per_thread = NSMEM_S1 * NL * 4;
     static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
-    static constexpr int STRIDE = fit > 768 ? 768 : fit;          // max threads per block = lane stride
+    // dual-product micro-ops (NL <= 16) want ~150 registers: at most 384 threads per block
+    static constexpr int cap = (NL <= 16) ? 384 : 768;
+    static constexpr int STRIDE = fit > cap ? cap : fit;          // max threads per block = lane stride
     static constexpr int smem = per_thread * STRIDE;
 };
 

@@ -118,6 +118,58 @@ __device__ __forceinline__ void mont_mul(uint32_t (&r)[NL], const uint32_t (&a)[
     for (int k = 0; k < NL; k++) r[k] = take ? d[k] : t[k];
 }
 
+// Two independent products at once, rows interleaved: (r0,r1) = (a0*b0, a1*b1) * R^-1 mod N.
+// Same arithmetic as mont_mul; writing the rows alternately hands ptxas twice as many independent
+// IMAD.WIDE carry chains (and two independent reduction tails), which is what hides the
+// fixed-latency stalls when only ~3 warps share a sub-partition.
+template <int NL>
+__device__ __forceinline__ void mont_mul2(uint32_t (&r0)[NL], const uint32_t (&a0)[NL], const uint32_t (&b0)[NL],
+                                          uint32_t (&r1)[NL], const uint32_t (&a1)[NL], const uint32_t (&b1)[NL],
+                                          const ModParams<NL> &P)
+{
+    constexpr int W = MontW<NL>::W;
+    uint32_t X0[W], Y0[W], X1[W], Y1[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) { X0[k] = 0; Y0[k] = 0; X1[k] = 0; Y1[k] = 0; }
+    auto row = [&](uint32_t (&Eo)[W], uint32_t (&Oo)[W], const uint32_t (&a)[NL], uint32_t bi) {
+        uint32_t e1 = Eo[1];
+#pragma unroll
+        for (int k = 0; k < W - 2; k++) Eo[k] = Eo[k + 2];
+        Eo[W - 2] = 0; Eo[W - 1] = 0;
+        add_cc(Oo[0], e1);
+        if (NL > 1) mad_row<NL, W, 1, true>(Eo, a, bi);
+        else { addc_cc(Eo[0], 0); addc(Eo[1], 0); }
+        mad_row<NL, W, 0, false>(Oo, a, bi);
+        uint32_t m = mul_lo(Oo[0], P.m0inv);
+        if (NL > 1) mad_row<NL, W, 1, false>(Eo, P.n, m);
+        mad_row<NL, W, 0, false>(Oo, P.n, m);
+    };
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+        if ((i & 1) == 0) { row(X0, Y0, a0, b0[i]); row(X1, Y1, a1, b1[i]); }
+        else { row(Y0, X0, a0, b0[i]); row(Y1, X1, a1, b1[i]); }
+    }
+    auto finish = [&](uint32_t (&r)[NL], uint32_t (&X)[W], uint32_t (&Y)[W]) {
+        uint32_t t[NL + 1];
+        uint32_t (&E)[W] = (NL % 2 == 0) ? X : Y;
+        uint32_t (&O)[W] = (NL % 2 == 0) ? Y : X;
+        t[0] = add3_cc(E[1], O[0]);
+#pragma unroll
+        for (int k = 1; k < NL; k++) t[k] = addc3_cc(E[k + 1], O[k]);
+        t[NL] = addc3(E[NL + 1], O[NL]);
+        uint32_t d[NL];
+        d[0] = sub3_cc(t[0], P.n[0]);
+#pragma unroll
+        for (int k = 1; k < NL; k++) d[k] = subc3_cc(t[k], P.n[k]);
+        uint32_t nb = subc3(t[NL], 0);
+        bool take = (nb != 0xffffffffu);
+#pragma unroll
+        for (int k = 0; k < NL; k++) r[k] = take ? d[k] : t[k];
+    };
+    finish(r0, X0, Y0);
+    finish(r1, X1, Y1);
+}
+
 template <int NL>
 __device__ __forceinline__ void mont_sqr(uint32_t (&r)[NL], const uint32_t (&a)[NL], const ModParams<NL> &P)
 {

@@ -20,23 +20,25 @@
 namespace ecmb200 {
 
 // ---- micro-ops --------------------------------------------------------------------------
-enum : uint32_t { U_MUL = 0, U_SQR = 1, U_ADD = 2, U_SUB = 3, U_ADDSUB = 4, U_COPY = 5, U_END = 15 };
+enum : uint32_t { U_MUL = 0, U_SQR = 1, U_ADD = 2, U_SUB = 3, U_ADDSUB = 4, U_COPY = 5, U_MUL2 = 6, U_END = 15 };
 // symbolic operands: 0..7 point coordinates resolved through the permutation, 8.. fixed slots
 enum : uint32_t { AX = 0, AZ, BX, BZ, CX, CZ, TX, TZ, S1 = 8, D1, S2, D2, SP, NSLOT_S1 };
 #define UOP(op, d, d2, x, y) ((uint32_t)(op) | ((uint32_t)(d) << 4) | ((uint32_t)(d2) << 8) | ((uint32_t)(x) << 12) | ((uint32_t)(y) << 16))
+// two independent multiplies in one micro-op: d = x*y and e = u*v (operands are all read before either result is written)
+#define UOP2(d, x, y, e, u, v) ((uint32_t)U_MUL2 | ((uint32_t)(d) << 4) | ((uint32_t)(x) << 12) | ((uint32_t)(y) << 16) | \
+                                ((uint32_t)(e) << 8) | ((uint32_t)(u) << 20) | ((uint32_t)(v) << 24))
 
 // vec_add(Pin -> Pout) with the current s1,d1,s2,d2; temporaries reuse d1 / s1 (dead after
 // their first use):  d1 = d1*s2 ; s1 = s1*d2 ; (d1,s1) = (d1+s1, d1-s1) ; d1 = d1^2 ; s1 = s1^2 ;
 // Pout.X = d1*Pin.Z ; Pout.Z = s1*Pin.X                                   (ecm.c:417-439)
 #define PROG_ADD(PinX, PinZ, PoutX, PoutZ)                                                     \
-    UOP(U_MUL, D1, 0, D1, S2), UOP(U_MUL, S1, 0, S1, D2), UOP(U_ADDSUB, D1, S1, D1, S1),         \
-    UOP(U_SQR, D1, 0, D1, D1), UOP(U_SQR, S1, 0, S1, S1), UOP(U_MUL, PoutX, 0, D1, PinZ),        \
-    UOP(U_MUL, PoutZ, 0, S1, PinX)
+    UOP2(D1, D1, S2, S1, S1, D2), UOP(U_ADDSUB, D1, S1, D1, S1), UOP2(D1, D1, D1, S1, S1, S1),    \
+    UOP2(PoutX, D1, PinZ, PoutZ, S1, PinX)
 // vec_duplicate(s,d -> P), scratch = a dead sum slot:  d = d^2 ; s = s^2 ; P.X = d*s ;
 // tmp = s-d ; s = tmp*sp ; s = s+d ; P.Z = s*tmp                           (ecm.c:447-454)
 #define PROG_DUP(s, d, tmp, PX, PZ)                                                            \
-    UOP(U_SQR, d, 0, d, d), UOP(U_SQR, s, 0, s, s), UOP(U_MUL, PX, 0, d, s), UOP(U_SUB, tmp, 0, s, d), \
-    UOP(U_MUL, s, 0, tmp, SP), UOP(U_ADD, s, 0, s, d), UOP(U_MUL, PZ, 0, s, tmp)
+    UOP2(d, d, d, s, s, s), UOP(U_SUB, tmp, 0, s, d), UOP2(PX, d, s, s, tmp, SP),                  \
+    UOP(U_ADD, s, 0, s, d), UOP(U_MUL, PZ, 0, s, tmp)
 #define PROG_SUMS(PX, PZ, s, d) UOP(U_ADDSUB, s, d, PX, PZ)
 
 // ---- stage-1 macro-ops (low 3 bits of the stream byte; high 5 bits = permutation index) ----
@@ -137,6 +139,26 @@ __device__ __forceinline__ void exec_uop(const SlotsT &S, uint32_t u, uint32_t p
     const uint32_t d = resolve((u >> 4) & 15u, permbits);
     const uint32_t x = resolve((u >> 12) & 15u, permbits);
     const uint32_t y = resolve((u >> 16) & 15u, permbits);
+    if (op == U_MUL2) {
+        const uint32_t e = resolve((u >> 8) & 15u, permbits);
+        const uint32_t x2 = resolve((u >> 20) & 15u, permbits);
+        const uint32_t y2 = resolve((u >> 24) & 15u, permbits);
+        if (NL <= 16) {                          // both products in flight: registers allow it
+            uint32_t a0[NL], b0[NL], a1[NL], b1[NL], r0[NL], r1[NL];
+            S.load(a0, x); S.load(b0, y); S.load(a1, x2); S.load(b1, y2);
+            mont_mul2<NL>(r0, a0, b0, r1, a1, b1, P);
+            S.store(d, r0); S.store(e, r1);
+        } else {                                 // wide operands: one after the other through the same body
+            uint32_t a0[NL], b0[NL], r0[NL];
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                S.load(a0, h ? x2 : x); S.load(b0, h ? y2 : y);
+                mont_mul<NL>(r0, a0, b0, P);
+                S.store(h ? e : d, r0);
+            }
+        }
+        return;
+    }
     uint32_t a[NL], b[NL], r[NL];
     S.load(a, x);
     if (op == U_MUL || op == U_SQR) {

@@ -94,3 +94,37 @@ def test_stage2_program_counters_match_reference_printout(name):
     ref = g["counts"]
     assert {k: c[k] for k in ("s2_ptadds", "s2_numinv", "s2_paired", "pairmap_steps")} == \
            {k: ref[k] for k in ("s2_ptadds", "s2_numinv", "s2_paired", "pairmap_steps")}
+
+
+CLI = os.path.join(ROOT, "avx-ecm_b200", "avx-ecm-b200")
+
+
+def _fib(n):
+    a, b = 0, 1
+    for _ in range(n):
+        a, b = b, a + b
+    return a
+
+
+def _fact(n):
+    r = 1
+    for i in range(2, n + 1):
+        r *= i
+    return r
+
+
+@pytest.mark.parametrize("expr,value", [
+    ("fib(791)/13/677/216416017", _fib(791) // 13 // 677 // 216416017),
+    ("(2+110!)/446", (2 + _fact(110)) // 446),
+    ("(26*10^238-17)/(9*3*31*17914895525348997871953180891109)", (26 * 10 ** 238 - 17) // (9 * 3 * 31 * 17914895525348997871953180891109)),
+    ("((5801^61-1)/((5801-1)*4027*5763040637*48081214823351791*195790721913324330907*1811340220375495245599))",
+     (5801 ** 61 - 1) // ((5801 - 1) * 4027 * 5763040637 * 48081214823351791 * 195790721913324330907 * 1811340220375495245599)),
+    ("2^3^2", 512), ("7 - 2 - 1", 4), ("-3 + 10 % 4", -1), ("13# + gcd(12, 18) + 1<<4", (30030 + 6 + 1) << 4),
+    ("modexp(3, 100, 1000007) + sqrt(1000000) + lg2(1024)", pow(3, 100, 1000007) + 1000 + 11),
+    ("0x10 * 2", 32),
+])
+def test_cli_expression_evaluator_matches_python(expr, value):
+    # the inputs of the reference's test.csh use this expression language (calc.c)
+    import subprocess
+    out = subprocess.run([CLI, "--eval", expr], capture_output=True, text=True, check=True).stdout.strip()
+    assert int(out) == value

@@ -66,3 +66,24 @@ def test_stage2_many_curves_spanning_blocks():
     for i in (0, 287, 288, 699):
         o = O.ecm_curve(N, b1, b2, 1000 + i)
         assert r["acc"][i] == o["acc"] and r["x"][i] == o["x"]
+
+
+def test_cli_writes_reference_files(tmp_path):
+    """The command-line driver (avx-ecm's argv contract) appends the reference's save_b1.txt lines byte
+    for byte and reports the same factors in ecm_results.txt."""
+    import os, re, subprocess
+    from conftest import ROOT
+    cli = os.path.join(ROOT, "avx-ecm_b200", "avx-ecm-b200")
+    for name in ("readme508_b1_5e4", "small96_D210"):
+        g = GOLDEN[name]
+        d = tmp_path / name
+        d.mkdir()
+        expr = "fib(791)/13/677/216416017" if name.startswith("readme") else g["n"]
+        out = subprocess.run([cli, expr, str(len(g["save_lines"])), str(g["b1"]), "1", str(g["b2"]), g["sigma0"]],
+                             cwd=d, capture_output=True, text=True, check=True).stdout
+        assert open(d / "save_b1.txt").read() == "".join(g["save_lines"])
+        got = set()
+        res = (d / "ecm_results.txt").read_text() if (d / "ecm_results.txt").exists() else ""
+        for m in re.finditer(r"found \S+ factor (\d+) in stage (\d) .*sigma (\d+)", res):
+            got.add((m.group(3), int(m.group(2)), m.group(1)))
+        assert got == {(f["sigma"], f["stage"], f["factor"]) for f in g["factors"]}
