@@ -268,6 +268,7 @@ def main():
     value = total_curve_equiv / dev_s
     prod_rate = value * MODMUL_PER_CURVE * W          # algorithmic products / s over all GPUs
     peak_all = allsum(peak_prod)
+    total_launches = int(allsum(launches))            # collective: every rank must take part
 
     # ---- e2e: the complete job through the C ABI with host buffers --------------------------------
     e2e = None
@@ -299,6 +300,25 @@ def main():
         if not check:
             raise SystemExit("bench.py: stage-1 residue of sigma=%d differs from the oracle" % sig[0])
 
+    # ---- the metric's second operand size: 1024-bit N, same B1, a few launches of the same schedule ----
+    also = None
+    if rank == 0 and not args.no_e2e:
+        N2 = int(json.load(open(os.path.join(ROOT, "tests", "golden", "composites.json")))["syn1024"])
+        c2 = E.EcmContext(N2, curves, device=local_rank)
+        c2.build_curves(sig)
+        c2.stage1_begin(B1)
+        tot2, _ = c2.stage1_launches()
+        c2.stage1_step(1); c2.sync()
+        c2.build_curves(sig); c2.stage1_begin(B1)
+        c2.timer_start(); c2.stage1_step(3); frac2 = c2.stage1_progress(); c2.timer_stop(); c2.sync()
+        ms2 = c2.timer_ms()
+        v2 = curves * frac2 / (ms2 / 1e3)
+        W2 = 2 * c2.nl * c2.nl + c2.nl
+        also = {"stage1_curves_per_sec_B1_1e6_1024bit": v2, "limbs": c2.nl, "launches_timed": 3, "launches_per_full_job": tot2,
+                "products_per_sec": v2 * MODMUL_PER_CURVE * W2, "frac_of_imad_peak": v2 * MODMUL_PER_CURVE * W2 / peak_prod,
+                "composite": "syn1024", "curves": curves}
+        c2.close()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, kind, cores, desc = run_reference_sample(B1, host_threads())
@@ -314,12 +334,14 @@ def main():
                        "step": "one kernel launch of the stage-1 schedule", "steps_per_full_job": steps_per_job,
                        "job_fraction_timed": done_frac, "l2": "256 MiB memset between steps (inside the timed region)",
                        "residue_check_vs_oracle": check},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(allsum(launches)) if dist else int(launches),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches,
             "roofline": {"bound": "imad", "achieved": prod_rate / 1e9, "peak": peak_all / 1e9, "unit": "Gprod/s",
                          "frac": prod_rate / peak_all, "traffic": None,
-                         "note": "achieved = curves/s x 12974547 modmul/curve x (2n^2+n) products, n=%d; peak = IMAD.WIDE.U32.X chains "
-                                 "measured live on this GPU (%.0f MHz)" % (nl, peak_clk)},
+                         "note": "achieved = curves/s x 12974547 modmul/curve x (2n^2+n) products, n=%d; peak = fastest of three live probes on this GPU "
+                                 "(IMAD.WIDE.U32.X chains with uniform / per-thread multiplier, register-resident 32-limb Montgomery loop) "
+                                 "at %.0f MHz; the pipe's arithmetic ceiling is 32 products/clk/SM" % (nl, peak_clk)},
             "cpu_baseline": cpu_baseline,
+            "also": also,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
