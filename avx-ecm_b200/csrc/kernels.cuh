@@ -235,13 +235,9 @@ __global__ void k_fieldop(const ModParams<NL> P, const ModParams<NL> *Pg, int op
     nm_mul<NL>(b, b, Pg->r2, Pg);
 #pragma unroll 1
     for (int it = 0; it < repeat; it++) {
-        if (op <= 1) {
-            if (op == 1) {
-#pragma unroll
-                for (int k = 0; k < NL; k++) b[k] = a[k];
-            }
-            mont_mul<NL>(r, a, b, P);
-        } else if (op == 2) mod_add<NL>(r, a, b, P);
+        if (op == 0) mont_mul<NL>(r, a, b, P);
+        else if (op == 1) mont_sqr<NL>(r, a, P);
+        else if (op == 2) mod_add<NL>(r, a, b, P);
         else mod_sub<NL>(r, a, b, P);
 #pragma unroll
         for (int k = 0; k < NL; k++) a[k] = r[k];
@@ -306,7 +302,11 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
         const uint64_t ins = __ldg(code + i);
         const uint32_t lo = (uint32_t)ins, imm = (uint32_t)(ins >> 32);
         const uint32_t op = lo & 0xffu, d = (lo >> 8) & 0xffu, x = (lo >> 16) & 0xffu, y = lo >> 24;
-        if (op <= V2_SQR || op == V2_PAIR) {
+        if (op == V2_SQR && UseSqr<NL>::value) {
+            S.load(a, x);
+            mont_sqr<NL>(r, a, P);
+            S.store(d, r);
+        } else if (op <= V2_SQR || op == V2_PAIR) {
             uint32_t dst = d;
             if (op == V2_PAIR) {                         // acc *= Pa_inv[pa] - Pb[pb].X  (ecm.c:1857-1859)
                 uint32_t u[NL], v[NL];

@@ -152,8 +152,10 @@ __device__ __forceinline__ void exec_uop(const SlotsT &S, uint32_t u, uint32_t p
             uint32_t a0[NL], b0[NL], r0[NL];
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
-                S.load(a0, h ? x2 : x); S.load(b0, h ? y2 : y);
-                mont_mul<NL>(r0, a0, b0, P);
+                const uint32_t xs = h ? x2 : x, ys = h ? y2 : y;
+                S.load(a0, xs);
+                if (xs == ys && UseSqr<NL>::value) mont_sqr<NL>(r0, a0, P);
+                else { S.load(b0, ys); mont_mul<NL>(r0, a0, b0, P); }
                 S.store(h ? e : d, r0);
             }
         }
@@ -162,7 +164,6 @@ __device__ __forceinline__ void exec_uop(const SlotsT &S, uint32_t u, uint32_t p
     uint32_t a[NL], b[NL], r[NL];
     S.load(a, x);
     if (op == U_MUL || op == U_SQR) {
-        // one shared multiply body serves both (dedicated squaring: see DESIGN.md roadmap)
         S.load(b, y);
         mont_mul<NL>(r, a, b, P);
         S.store(d, r);
