@@ -7,6 +7,8 @@
 #include "plan2.hpp"
 #include <cuda_runtime.h>
 #include <atomic>
+#include <thread>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -416,11 +418,12 @@ int ecm_b200_read_stage1(ecm_b200_ctx *c, uint32_t *x, uint32_t *z, uint8_t *fac
     return ECM_B200_OK;
 }
 
-// Run one compiled stage-2 program over a wave of `groups` curve groups with the same round-robin
-// (group, chunk) schedule as stage 1.
-static int run_program(ecm_b200_ctx *c, const uint64_t *d_code, uint64_t ncode, uint32_t *state2, uint32_t cap2, uint32_t *tab,
-                       uint32_t groups, uint8_t *inv_fail)
+// Generic part of a stage-2 program: the slot-file machine over a wave of `groups` curve groups with the
+// same round-robin (group, chunk) schedule as stage 1.
+static int run_vm2(ecm_b200_ctx *c, const uint64_t *d_code, uint64_t ncode, uint32_t *state2, uint32_t cap2, uint32_t *tab,
+                   uint32_t groups, uint8_t *inv_fail)
 {
+    if (ncode == 0) return ECM_B200_OK;
     const uint32_t chunk = 65536;
     const uint64_t nchunks = (ncode + chunk - 1) / chunk;
     const uint64_t items = nchunks * groups;
@@ -435,19 +438,66 @@ static int run_program(ecm_b200_ctx *c, const uint64_t *d_code, uint64_t ncode, 
     return ECM_B200_OK;
 }
 
+// A compiled program is dispatched in segments: maximal runs of pair steps go to the register-resident
+// pair kernel, everything else (window builds, inversions, ladders) to the slot-file machine.
+static int run_program(ecm_b200_ctx *c, const std::vector<uint64_t> &host_code, const uint64_t *d_code, uint32_t *state2,
+                       uint32_t cap2, uint32_t *tab, uint32_t groups, uint32_t ncurves, uint8_t *inv_fail)
+{
+    const uint64_t n = host_code.size();
+    const uint32_t kMinRun = 16;
+    uint64_t seg = 0, i = 0;
+    while (i < n) {
+        if ((host_code[i] & 0xff) == V_PAIR) {
+            uint64_t j = i;
+            while (j < n && (host_code[j] & 0xff) == V_PAIR) j++;
+            if (j - i >= kMinRun) {
+                int rc = run_vm2(c, d_code + seg, i - seg, state2, cap2, tab, groups, inv_fail);
+                if (rc) return rc;
+                {   // chunk-major (group, chunk) items, at most one resident wave per launch
+                    const uint32_t TP = (uint32_t)c->eng->threads_pair, npairs = (uint32_t)(j - i);
+                    const uint32_t pgroups = (ncurves + TP - 1) / TP, pchunk = 512;
+                    const uint64_t items = (uint64_t)((npairs + pchunk - 1) / pchunk) * pgroups;
+                    const uint32_t per = std::min<uint32_t>(pgroups, (uint32_t)(c->num_sms * c->eng->pair_blocks_per_sm));
+                    for (uint64_t it = 0; it < items;) {
+                        const uint32_t blocks = (uint32_t)std::min<uint64_t>(per, items - it);
+                        c->eng->pair_run(c->stream, blocks, state2, cap2, tab, d_code + i, npairs, ncurves, pchunk, pgroups, it);
+                        c->s2_launches++;
+                        it += blocks;
+                    }
+                }
+                seg = j;
+            }
+            i = j;
+        } else i++;
+    }
+    return run_vm2(c, d_code + seg, n - seg, state2, cap2, tab, groups, inv_fail);
+}
+
 int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
 {
     if (!c) return fail(ECM_B200_EINVAL, "null context");
     if (!c->have_curves) return fail(ECM_B200_ESTATE, "no curves loaded");
     if (b2 <= b1) return fail(ECM_B200_EINVAL, "B2 must exceed B1 (B2 <= B1 disables stage 2, main.c:548-552)");
     CU(cudaSetDevice(c->device));
-    // ---- compile (host): ecm_stage2_init + one ecm_stage2_pair program per 1e8 prime range (ecm.c:1424-1476)
+    // ---- compile (host): ecm_stage2_init now; the per-range ecm_stage2_pair programs (sieve + PAIR, about
+    // 2.5 s per 1e8 primes) are compiled by a background thread while the GPU already executes the init
+    // program and the earlier ranges (ecm.c:1424-1476 does this serially on the main thread).
+    const uint64_t PRIME_RANGE = 100000000ull;
+    std::vector<std::pair<uint64_t, uint64_t>> rng;
+    for (uint64_t p = b1; p < b2; p += PRIME_RANGE) rng.push_back({p, std::min(p + PRIME_RANGE, b2)});
+    std::atomic<int> nready{(int)rng.size()};
+    std::thread planner;
     if (c->prog2_b1 != b1 || c->prog2_b2 != b2) {
         plan_stage2_init(b1, c->prog2);
-        const uint64_t PRIME_RANGE = 100000000ull;
-        for (uint64_t p = b1; p < b2; p += PRIME_RANGE) plan_stage2_range(p, std::min(p + PRIME_RANGE, b2), c->prog2);
+        c->prog2.ranges.assign(rng.size(), std::vector<uint64_t>());
+        nready = 0;
+        Stage2Program *pp = &c->prog2;
+        planner = std::thread([pp, rng, &nready]() {
+            for (size_t r = 0; r < rng.size(); r++) { plan_stage2_range(rng[r].first, rng[r].second, *pp, (int)r); nready.fetch_add(1, std::memory_order_release); }
+        });
         c->prog2_b1 = b1; c->prog2_b2 = b2;
     }
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{planner};
     const Stage2Program &pg = c->prog2;
     const int nl = c->nl;
     const uint32_t T = c->eng->threads_s2;
@@ -455,8 +505,14 @@ int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
     const size_t per_curve = ((size_t)pg.lay.entries + c->eng->nslot_s2) * nl * 4 + 1;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
+    // device buffer for the largest program: a range never has more instructions than
+    // (#primes <= span/8 for span >= 1e5) + 1300 per window shift + ladder/window set-up
     size_t code_bytes = pg.init.size() * 8;
-    for (const auto &r : pg.ranges) code_bytes = std::max(code_bytes, r.size() * 8);
+    for (const auto &r : rng) {
+        const uint64_t span = r.second - r.first;
+        const uint64_t bound = span / 6 + (span / ((uint64_t)pg.prm.D * pg.prm.U * 2) + 2) * 1300 + 200000;
+        code_bytes = std::max<size_t>(code_bytes, bound * 8);
+    }
     const size_t budget = (size_t)((double)free_b * 0.90) - std::min<size_t>(code_bytes + (64u << 20), free_b / 4);
     uint32_t cap2 = (uint32_t)std::min<size_t>((c->count + T - 1) / T * T, budget / per_curve / T * T);
     if (cap2 < T) return fail(ECM_B200_ENOMEM, "not enough device memory for one stage-2 group");
@@ -476,11 +532,14 @@ int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
         c->eng->s2_setup(c->stream, c->d_state, c->G1, 2 * c->p_slot, 2 * c->p_slot + 1, SP, first, c->count, state2, cap2, tab,
                          pg.lay.qx, pg.lay.qz, wfail);
         CUS(cudaMemcpyAsync(d_code, pg.init.data(), pg.init.size() * 8, cudaMemcpyHostToDevice, c->stream));
-        int rc = run_program(c, d_code, pg.init.size(), state2, cap2, tab, groups, wfail);
+        int rc = run_program(c, pg.init, d_code, state2, cap2, tab, groups, n, wfail);
         if (rc) { cleanup(); return rc; }
-        for (const auto &r : pg.ranges) {
+        for (size_t ri = 0; ri < rng.size(); ri++) {
+            while (nready.load(std::memory_order_acquire) <= (int)ri) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+            const std::vector<uint64_t> &r = pg.ranges[ri];
+            if (r.size() * 8 > code_bytes) { cleanup(); return fail(ECM_B200_ENOMEM, "stage-2 program larger than its buffer bound"); }
             CUS(cudaMemcpyAsync(d_code, r.data(), r.size() * 8, cudaMemcpyHostToDevice, c->stream));
-            rc = run_program(c, d_code, r.size(), state2, cap2, tab, groups, wfail);
+            rc = run_program(c, r, d_code, state2, cap2, tab, groups, n, wfail);
             if (rc) { cleanup(); return rc; }
         }
         c->eng->s2_collect(c->stream, state2, cap2, wfail, first, n, c->count, c->d_acc, c->d_fail);

@@ -28,6 +28,9 @@ struct Engine {
     int threads_s2 = 0, smem_s2 = 0, nslot_s2 = 0;
     virtual void vm2(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, uint32_t *tab, const uint64_t *code,
                      uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0, uint8_t *inv_fail) = 0;
+    int threads_pair = 0, pair_blocks_per_sm = 1;
+    virtual void pair_run(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, const uint32_t *tab, const uint64_t *code,
+                          uint32_t npairs, uint32_t ncurves, uint32_t chunk_len, uint32_t groups, uint64_t item0) = 0;
     virtual void s2_setup(cudaStream_t st, const uint32_t *state1, Geom G1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
                           uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab, uint32_t e_qx,
                           uint32_t e_qz, uint8_t *inv_fail) = 0;

@@ -29,12 +29,22 @@ struct EngineT : Engine {
     {
         cudaError_t e = cudaFuncSetAttribute(k_stage1<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s1);
         if (e != cudaSuccess) return e;
+        threads_pair = PairCfg<NL>::THREADS;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pair_blocks_per_sm, k_pair<NL>, threads_pair, 0);
+        if (e != cudaSuccess) return e;
+        if (pair_blocks_per_sm < 1) pair_blocks_per_sm = 1;
         return cudaFuncSetAttribute(k_vm2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
     }
     void vm2(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, uint32_t *tab, const uint64_t *code,
              uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0, uint8_t *inv_fail) override
     {
         k_vm2<NL><<<blocks, threads_s2, smem_s2, st>>>(P, Pg, state2, cap, tab, code, ncode, chunk_len, groups, item0, inv_fail);
+        count_launch();
+    }
+    void pair_run(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, const uint32_t *tab, const uint64_t *code,
+                  uint32_t npairs, uint32_t ncurves, uint32_t chunk_len, uint32_t groups, uint64_t item0) override
+    {
+        k_pair<NL><<<blocks, PairCfg<NL>::THREADS, 0, st>>>(P, state2, cap, tab, code, npairs, ncurves, chunk_len, groups, item0);
         count_launch();
     }
     void s2_setup(cudaStream_t st, const uint32_t *state1, Geom G1, uint32_t xslot, uint32_t zslot, uint32_t spslot,

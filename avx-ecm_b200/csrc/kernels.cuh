@@ -17,7 +17,9 @@ template <int NL, int NSLOT>
 struct BlockCfg {
     static constexpr int per_thread = NSLOT * NL * 4;
     static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
-    static constexpr int THREADS = fit > 512 ? 512 : (fit < 32 ? 32 : fit);
+    // whole multiples of 4 warps keep the four sub-partitions evenly loaded
+    static constexpr int even = fit >= 128 ? fit / 128 * 128 : fit;
+    static constexpr int THREADS = even > 512 ? 512 : (even < 32 ? 32 : even);
     static constexpr int smem = per_thread * THREADS;
 };
 
@@ -32,6 +34,28 @@ __device__ __forceinline__ void gstore(uint32_t *state, uint32_t cap, uint32_t s
 {
 #pragma unroll
     for (int k = 0; k < NL; k++) state[((size_t)slot * NL + k) * cap + curve] = r[k];
+}
+
+// Stage-2 tables: entry e of curve c lives at tab[((e*nwg + c/32)*NL + limb)*32 + c%32]: the NL limbs of a
+// warp's 32 curves form one contiguous NL*128-byte block, so an operand costs one 64-bit address
+// computation and NL loads at immediate offsets, each a single 128-byte line.
+__device__ __forceinline__ size_t tab_base(uint32_t entry, uint32_t nwg, uint32_t curve, int NL)
+{
+    return (((size_t)entry * nwg + (curve >> 5)) * NL) * 32 + (curve & 31);
+}
+template <int NL>
+__device__ __forceinline__ void tload(uint32_t (&r)[NL], const uint32_t *tab, size_t base)
+{
+    const uint32_t *p = tab + base;
+#pragma unroll
+    for (int k = 0; k < NL; k++) r[k] = p[k * 32];
+}
+template <int NL>
+__device__ __forceinline__ void tstore(uint32_t *tab, size_t base, const uint32_t (&r)[NL])
+{
+    uint32_t *p = tab + base;
+#pragma unroll
+    for (int k = 0; k < NL; k++) p[k * 32] = r[k];
 }
 
 // ---- stage 1: interpret macro-ops [chunk*chunk_len, ...) for one group of blockDim.x curves ------
@@ -250,7 +274,7 @@ __global__ void k_fieldop(const ModParams<NL> P, const ModParams<NL> *Pg, int op
 // stage 2: the second field-op machine.  Same execution model as stage 1 (one thread = one curve,
 // slot file in shared memory, one op stream for the whole batch) with 64-bit instructions
 // compiled by plan2.cpp, global-memory point tables, a modular inverse and the fused pair step.
-// Table entry e of curve c: tab[(e*NL + limb)*cap + c].
+// Table entry e of curve c: see tab_base().
 // =================================================================================================
 enum : uint32_t { V2_MUL = 0, V2_SQR = 1, V2_ADD = 2, V2_SUB = 3, V2_ADDSUB = 4, V2_COPY = 5, V2_LDG = 6, V2_STG = 7,
                   V2_INV = 8, V2_ONE = 9, V2_PAIR = 10, V2_NOP = 11 };
@@ -290,6 +314,7 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
     const uint32_t g = (uint32_t)(item % groups);
     const uint64_t chunk = item / groups;
     const uint32_t curve = g * THREADS + threadIdx.x;
+    const uint32_t nwg = cap >> 5;
     Slots<NL, THREADS> S{smem + threadIdx.x};
     uint32_t a[NL], b[NL], r[NL];
 #pragma unroll 1
@@ -310,8 +335,8 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
             uint32_t dst = d;
             if (op == V2_PAIR) {                         // acc *= Pa_inv[pa] - Pb[pb].X  (ecm.c:1857-1859)
                 uint32_t u[NL], v[NL];
-                gload<NL>(u, tab, cap, imm & 0xffffu, curve);
-                gload<NL>(v, tab, cap, imm >> 16, curve);
+                tload<NL>(u, tab, tab_base(imm & 0xffffu, nwg, curve, NL));
+                tload<NL>(v, tab, tab_base(imm >> 16, nwg, curve, NL));
                 mod_sub<NL>(a, u, v, P);
                 S.load(b, V2_ACC);
                 dst = V2_ACC;
@@ -332,9 +357,9 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
         } else if (op == V2_COPY) {
             S.load(a, x); S.store(d, a);
         } else if (op == V2_LDG) {
-            gload<NL>(a, tab, cap, imm, curve); S.store(d, a);
+            tload<NL>(a, tab, tab_base(imm, nwg, curve, NL)); S.store(d, a);
         } else if (op == V2_STG) {
-            S.load(a, x); gstore<NL>(tab, cap, imm, curve, a);
+            S.load(a, x); tstore<NL>(tab, tab_base(imm, nwg, curve, NL), a);
         } else if (op == V2_INV) {
             vm2_inverse<NL, THREADS>(smem + threadIdx.x, d, x, Pg, inv_fail + curve);
         } else if (op == V2_ONE) {
@@ -345,6 +370,75 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
     }
 #pragma unroll 1
     for (uint32_t s = 0; s < NSLOT_S2; s++) { S.load(r, s); gstore<NL>(state2, cap, s, curve, r); }
+}
+
+// ---- the pair loop as its own kernel ----------------------------------------------------------------
+// Between two window shifts stage 2 is a long run of  acc *= Pa_inv[pa] - Pb[pb].X  (ecm.c:2526-2531,
+// 77 % of all stage-2 multiplies at B2 = 100*B1).  The run needs no slot file: the accumulator lives in
+// registers, the two operands stream from the tables ([entry][limb][curve], one 128-byte line per warp
+// and limb; Pa_inv is L2-resident, Pb comes from HBM), and for narrow moduli the next step's operands
+// are prefetched while the current product is computed.  No shared memory => 12-20 warps per SM.
+// code[i] is the 64-bit V2_PAIR instruction; only its imm half is read.
+template <int NL>
+struct PairCfg {
+    static constexpr bool DUAL = (NL <= 16);   // two accumulators per curve: twice the independent carry chains
+    static constexpr int THREADS = 128;        // 4 warps: one per SM sub-partition
+};
+
+// One block = one item = (group of 128 curves, chunk of the run), same chunk-major schedule as stage 1
+// so that every SM always holds its full complement of blocks even when the batch is not a multiple of
+// the resident wave.  The product of a run is commutative, so splitting it over two accumulators (and
+// re-joining them at the end of the chunk) yields the identical canonical residue.
+template <int NL>
+__global__ void __launch_bounds__(PairCfg<NL>::THREADS)
+k_pair(const ModParams<NL> P, uint32_t *__restrict__ state2, uint32_t cap, const uint32_t *__restrict__ tab,
+       const uint64_t *__restrict__ code, uint32_t npairs, uint32_t ncurves, uint32_t chunk_len, uint32_t groups, uint64_t item0)
+{
+    const uint64_t item = item0 + blockIdx.x;
+    const uint32_t g = (uint32_t)(item % groups);
+    const uint32_t chunk = (uint32_t)(item / groups);
+    const uint32_t curve = g * PairCfg<NL>::THREADS + threadIdx.x;
+    if (curve >= ncurves) return;
+    uint32_t i = chunk * chunk_len;
+    const uint32_t end = (i + chunk_len < npairs) ? i + chunk_len : npairs;
+    const uint32_t nwg = cap >> 5;
+    if (PairCfg<NL>::DUAL) {
+        uint32_t acc0[NL], acc1[NL], t0[NL], t1[NL], v[NL];
+        gload<NL>(acc0, state2, cap, V2_ACC, curve);
+#pragma unroll
+        for (int k = 0; k < NL; k++) acc1[k] = P.one[k];
+#pragma unroll 1
+        for (; i < end; i += 2) {
+            const uint32_t imm0 = (uint32_t)(__ldg(code + i) >> 32);
+            tload<NL>(t0, tab, tab_base(imm0 & 0xffffu, nwg, curve, NL));
+            tload<NL>(v, tab, tab_base(imm0 >> 16, nwg, curve, NL));
+            mod_sub<NL>(t0, t0, v, P);
+            if (i + 1 < end) {
+                const uint32_t imm1 = (uint32_t)(__ldg(code + i + 1) >> 32);
+                tload<NL>(t1, tab, tab_base(imm1 & 0xffffu, nwg, curve, NL));
+                tload<NL>(v, tab, tab_base(imm1 >> 16, nwg, curve, NL));
+                mod_sub<NL>(t1, t1, v, P);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NL; k++) t1[k] = P.one[k];
+            }
+            mont_mul2<NL>(acc0, acc0, t0, acc1, acc1, t1, P);
+        }
+        mont_mul<NL>(acc0, acc0, acc1, P);
+        gstore<NL>(state2, cap, V2_ACC, curve, acc0);
+    } else {
+        uint32_t acc[NL], u[NL], v[NL];
+        gload<NL>(acc, state2, cap, V2_ACC, curve);
+#pragma unroll 1
+        for (; i < end; i++) {
+            const uint32_t imm = (uint32_t)(__ldg(code + i) >> 32);
+            tload<NL>(u, tab, tab_base(imm & 0xffffu, nwg, curve, NL));
+            tload<NL>(v, tab, tab_base(imm >> 16, nwg, curve, NL));
+            mod_sub<NL>(u, u, v, P);
+            mont_mul<NL>(acc, acc, u, P);
+        }
+        gstore<NL>(state2, cap, V2_ACC, curve, acc);
+    }
 }
 
 // stage-2 wave set-up: Q = stage-1 result and the curve parameter move from the stage-1 state into
@@ -359,8 +453,8 @@ __global__ void k_s2_setup(const uint32_t *state1, Geom G1, uint32_t xslot, uint
     if (c >= cap2) return;
     uint32_t src = first + c; if (src >= count) src = count - 1;
     for (int k = 0; k < NL; k++) {
-        tab[((size_t)e_qx * NL + k) * cap2 + c] = state1[G1.idx(src, xslot, k, NL)];
-        tab[((size_t)e_qz * NL + k) * cap2 + c] = state1[G1.idx(src, zslot, k, NL)];
+        tab[tab_base(e_qx, cap2 >> 5, c, NL) + (size_t)k * 32] = state1[G1.idx(src, xslot, k, NL)];
+        tab[tab_base(e_qz, cap2 >> 5, c, NL) + (size_t)k * 32] = state1[G1.idx(src, zslot, k, NL)];
         for (uint32_t s = 0; s < NSLOT_S2; s++)
             state2[((size_t)s * NL + k) * cap2 + c] = (s == V2_SP) ? state1[G1.idx(src, spslot, k, NL)] : 0;
     }

@@ -193,14 +193,15 @@ void plan_stage2_init(uint64_t b1, Stage2Program &prog)
 }
 
 // ecm_stage2_pair (ecm.c:2342-2540) for the primes of [lo,hi)
-void plan_stage2_range(uint64_t lo, uint64_t hi, Stage2Program &prog)
+void plan_stage2_range(uint64_t lo, uint64_t hi, Stage2Program &prog, int index)
 {
     const Stage2Params &p = prog.prm;
     const Stage2Layout &L = prog.lay;
     const std::vector<uint32_t> map = stage2_map(p, nullptr);
     const uint32_t w = p.D, U = p.U, win = 2 * p.L;
-    prog.ranges.emplace_back();
-    Asm a{prog.ranges.back()};
+    if (index < 0) { prog.ranges.emplace_back(); index = (int)prog.ranges.size() - 1; }
+    prog.ranges[index].clear();
+    Asm a{prog.ranges[index]};
 
     std::vector<uint32_t> pm_v, pm_u;
     uint32_t amin_final = 0, npairs = 0;

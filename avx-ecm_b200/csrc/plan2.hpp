@@ -51,7 +51,9 @@ struct Stage2Program {
 
 Stage2Layout stage2_layout(const Stage2Params &p);
 void plan_stage2_init(uint64_t b1, Stage2Program &prog);
-// appends the program of one prime range [lo,hi) (lo = B1 for the first); amin restarts per range
-void plan_stage2_range(uint64_t lo, uint64_t hi, Stage2Program &prog);
+// compiles the program of one prime range [lo,hi) (lo = B1 for the first; amin restarts per range) into
+// prog.ranges[index] (index < 0: append).  Ranges may be compiled by a background thread while the GPU
+// executes the previous one; the counters are only meaningful once all ranges are done.
+void plan_stage2_range(uint64_t lo, uint64_t hi, Stage2Program &prog, int index = -1);
 
 }  // namespace ecmb200
