@@ -263,7 +263,9 @@ int ecm_b200_stage1_begin(ecm_b200_ctx *c, uint64_t b1)
 {
     if (!c) return fail(ECM_B200_EINVAL, "null context");
     if (!c->have_curves) return fail(ECM_B200_ESTATE, "no curves loaded");
-    if (b1 < 2 || b1 > 4000000000ull) return fail(ECM_B200_EINVAL, "B1 out of range");
+    // one prime range only: beyond 1e8 the reference restarts ecm_stage1 per range (repeating the powers of
+    // two and skipping each range's first prime, ecm.c:1209-1234,1815-1824); that quirk is not reproduced
+    if (b1 < 2 || b1 > 100000000ull) return fail(ECM_B200_EINVAL, "B1 out of range (2 .. 1e8)");
     CU(cudaSetDevice(c->device));
     if (c->plan.b1 != b1) { plan_stage1(b1, c->plan); c->plan_on_device = false; }
     if (!c->plan_on_device) {
@@ -275,7 +277,7 @@ int ecm_b200_stage1_begin(ecm_b200_ctx *c, uint64_t b1)
         CU(cudaMemcpyAsync(c->d_ops, c->plan.ops.data(), c->plan.ops.size(), cudaMemcpyHostToDevice, c->stream));
         c->plan_on_device = true;
     }
-    if (c->p_slot != 0) return fail(ECM_B200_ESTATE, "stage 1 already run on this batch");
+    if (c->stage1_done) return fail(ECM_B200_ESTATE, "stage 1 already run on this batch");
     // Schedule: an item is (group of THREADS curves, chunk of the op stream).  Items are ordered
     // chunk-major and a launch takes a run of consecutive items, at most one per SM; because a run
     // is never longer than the number of groups, item (g, c-1) is always in an earlier launch.
@@ -516,6 +518,11 @@ int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
     const size_t budget = (size_t)((double)free_b * 0.90) - std::min<size_t>(code_bytes + (64u << 20), free_b / 4);
     uint32_t cap2 = (uint32_t)std::min<size_t>((c->count + T - 1) / T * T, budget / per_curve / T * T);
     if (cap2 < T) return fail(ECM_B200_ENOMEM, "not enough device memory for one stage-2 group");
+    {   // several waves: make them equal instead of one full wave plus a small remainder
+        const uint32_t waves = (c->count + cap2 - 1) / cap2;
+        const uint32_t even = ((c->count + waves - 1) / waves + T - 1) / T * T;
+        if (even < cap2) cap2 = even;
+    }
     uint32_t *tab = nullptr, *state2 = nullptr; uint8_t *wfail = nullptr; uint64_t *d_code = nullptr;
     auto cleanup = [&]() { cudaFree(tab); cudaFree(state2); cudaFree(wfail); cudaFree(d_code); };
 #define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ECM_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)

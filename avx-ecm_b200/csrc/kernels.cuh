@@ -61,7 +61,9 @@ __device__ __forceinline__ void tstore(uint32_t *tab, size_t base, const uint32_
 // ---- stage 1: interpret macro-ops [chunk*chunk_len, ...) for one group of blockDim.x curves ------
 template <int NL>
 struct S1Cfg {
-    static constexpr int per_thread = NSMEM_S1 * NL * 4;
+    // wide moduli stream their operands from shared memory and need two staging slots for point operands
+    static constexpr int nsmem = (NL > 32) ? NSMEM_S1 + 2 : NSMEM_S1;
+    static constexpr int per_thread = nsmem * NL * 4;
     static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
     // dual-product micro-ops (NL <= 16) want ~150 registers: at most 384 threads per block
     static constexpr int cap = (NL <= 16) ? 384 : 768;

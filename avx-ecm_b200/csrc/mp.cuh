@@ -354,6 +354,96 @@ __device__ __forceinline__ void mod_sub(uint32_t (&r)[NL], const uint32_t (&a)[N
     if (NL == 1) { /* add3_cc already final */ }
 }
 
+// ---- wide moduli (NL > 32): operands streamed from shared memory ------------------------------------
+// Holding a (NL), b (NL) and the two accumulators (2NL+4) in registers no longer fits at 48/64 limbs
+// (the compiler spills and the multiply drops to 0.4 of the roof).  Here only the accumulators are
+// register-resident; a[j] and b[i] are read from the slot file when needed (NL^2 + NL shared loads per
+// multiply against 2NL^2 IMAD.WIDE: the LSU is ~50 % busy) and the reduction tail works in place.
+template <int STRIDE>
+struct SmemLimbs {
+    const uint32_t *p;
+    __device__ __forceinline__ uint32_t operator[](int j) const { return p[j * STRIDE]; }
+};
+
+// canonical result of T' = (E>>32) + O (< 2N), written limb by limb through `put(k, value)`
+template <int NL, int W, class PUT>
+__device__ __forceinline__ void mont_tail_inplace(uint32_t (&E)[W], uint32_t (&O)[W], const ModParams<NL> &P, PUT put)
+{
+    add_cc(O[0], E[1]);
+#pragma unroll
+    for (int k = 1; k < NL; k++) addc_cc(O[k], E[k + 1]);
+    addc(O[NL], E[NL + 1]);
+    // does T' >= N ?  (borrow of T' - N, results discarded)
+    (void)sub3_cc(O[0], P.n[0]);
+#pragma unroll
+    for (int k = 1; k < NL; k++) (void)subc3_cc(O[k], P.n[k]);
+    const uint32_t nb = subc3(O[NL], 0);
+    const uint32_t mask = (nb != 0xffffffffu) ? 0xffffffffu : 0u;
+    uint32_t v = sub3_cc(O[0], P.n[0] & mask);
+    put(0, v);
+#pragma unroll
+    for (int k = 1; k < NL; k++) { v = (k == NL - 1) ? subc3(O[k], P.n[k] & mask) : subc3_cc(O[k], P.n[k] & mask); put(k, v); }
+}
+
+template <int NL, class AT, class BT, class PUT>
+__device__ __forceinline__ void mont_mul_stream(const AT &a, const BT &b, const ModParams<NL> &P, PUT put)
+{
+    constexpr int W = MontW<NL>::W;
+    uint32_t X[W], Y[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) { X[k] = 0; Y[k] = 0; }
+    auto row = [&](uint32_t (&Eo)[W], uint32_t (&Oo)[W], uint32_t bi) {
+        uint32_t e1 = Eo[1];
+#pragma unroll
+        for (int k = 0; k < W - 2; k++) Eo[k] = Eo[k + 2];
+        Eo[W - 2] = 0; Eo[W - 1] = 0;
+        add_cc(Oo[0], e1);
+        mad_row<NL, W, 1, true>(Eo, a, bi);
+        mad_row<NL, W, 0, false>(Oo, a, bi);
+        uint32_t m = mul_lo(Oo[0], P.m0inv);
+        mad_row<NL, W, 1, false>(Eo, P.n, m);
+        mad_row<NL, W, 0, false>(Oo, P.n, m);
+    };
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+        if ((i & 1) == 0) row(X, Y, b[i]); else row(Y, X, b[i]);
+    }
+    if (NL % 2 == 0) mont_tail_inplace<NL, W>(X, Y, P, put); else mont_tail_inplace<NL, W>(Y, X, P, put);
+}
+
+// (a+b) mod N and (a-b) mod N with streamed operands, canonical
+template <int NL, class AT, class BT, class PUT>
+__device__ __forceinline__ void mod_add_stream(const AT &a, const BT &b, const ModParams<NL> &P, PUT put)
+{
+    uint32_t t[NL];
+    t[0] = add3_cc(a[0], b[0]);
+#pragma unroll
+    for (int k = 1; k < NL; k++) t[k] = addc3_cc(a[k], b[k]);
+    const uint32_t c = addc3(0, 0);
+    (void)sub3_cc(t[0], P.n[0]);
+#pragma unroll
+    for (int k = 1; k < NL; k++) (void)subc3_cc(t[k], P.n[k]);
+    const uint32_t nb = subc3(c, 0);
+    const uint32_t mask = (nb != 0xffffffffu) ? 0xffffffffu : 0u;
+    uint32_t v = sub3_cc(t[0], P.n[0] & mask);
+    put(0, v);
+#pragma unroll
+    for (int k = 1; k < NL; k++) { v = (k == NL - 1) ? subc3(t[k], P.n[k] & mask) : subc3_cc(t[k], P.n[k] & mask); put(k, v); }
+}
+template <int NL, class AT, class BT, class PUT>
+__device__ __forceinline__ void mod_sub_stream(const AT &a, const BT &b, const ModParams<NL> &P, PUT put)
+{
+    uint32_t t[NL];
+    t[0] = sub3_cc(a[0], b[0]);
+#pragma unroll
+    for (int k = 1; k < NL; k++) t[k] = subc3_cc(a[k], b[k]);
+    const uint32_t bo = subc3(0, 0);
+    uint32_t v = add3_cc(t[0], P.n[0] & bo);
+    put(0, v);
+#pragma unroll
+    for (int k = 1; k < NL; k++) { v = (k == NL - 1) ? addc3(t[k], P.n[k] & bo) : addc3_cc(t[k], P.n[k] & bo); put(k, v); }
+}
+
 // 1 if a == 0
 template <int NL>
 __device__ __forceinline__ bool is_zero(const uint32_t (&a)[NL])

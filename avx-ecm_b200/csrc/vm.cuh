@@ -104,6 +104,21 @@ template <int NL, int STRIDE>
 struct HybridSlots {
     uint32_t *gl;     // state of this block's group + threadIdx.x
     uint32_t *sm;     // smem + threadIdx.x
+    // wide moduli: pointer to a slot's limbs (stride STRIDE words); global slots are first copied into
+    // one of two shared staging slots (shared indices 5 and 6)
+    __device__ __forceinline__ uint32_t *ptr(uint32_t slot) const
+    {
+        return slot < 8 ? gl + slot * (NL * STRIDE) : sm + (slot - 8) * (NL * STRIDE);
+    }
+    __device__ __forceinline__ const uint32_t *operand(uint32_t slot, int staging) const
+    {
+        if (slot >= 8) return sm + (slot - 8) * (NL * STRIDE);
+        uint32_t *dst = sm + (5 + staging) * (NL * STRIDE);
+        const uint32_t *src = gl + slot * (NL * STRIDE);
+#pragma unroll 8
+        for (int k = 0; k < NL; k++) dst[k * STRIDE] = src[k * STRIDE];
+        return dst;
+    }
     __device__ __forceinline__ void load(uint32_t (&r)[NL], uint32_t slot) const
     {
         if (slot < 8) {
@@ -130,6 +145,54 @@ struct HybridSlots {
     }
 };
 
+template <int NL, int STRIDE>
+__device__ __forceinline__ void exec_uop_stream(const HybridSlots<NL, STRIDE> &S, uint32_t u, uint32_t op, uint32_t d,
+                                                uint32_t x, uint32_t y, uint32_t permbits, const ModParams<NL> &P)
+{
+    if (op == U_MUL2 || op == U_MUL || op == U_SQR) {
+        const int n = (op == U_MUL2) ? 2 : 1;
+#pragma unroll 1
+        for (int h = 0; h < n; h++) {
+            const uint32_t xs = h ? resolve((u >> 20) & 15u, permbits) : x;
+            const uint32_t ys = h ? resolve((u >> 24) & 15u, permbits) : y;
+            const uint32_t ds = h ? resolve((u >> 8) & 15u, permbits) : d;
+            // a stays in registers for the whole product, b[i] is fetched once per row
+            const uint32_t *pa = S.ptr(xs);
+            uint32_t areg[NL];
+#pragma unroll
+            for (int k = 0; k < NL; k++) areg[k] = pa[k * STRIDE];
+            SmemLimbs<STRIDE> B{S.operand(ys, 1)};
+            uint32_t *dst = S.ptr(ds);
+            mont_mul_stream<NL>(areg, B, P, [&](int k, uint32_t val) { dst[k * STRIDE] = val; });
+        }
+    } else if (op == U_ADDSUB || op == U_ADD || op == U_SUB) {
+        SmemLimbs<STRIDE> A{S.operand(x, 0)}, B{S.operand(y, 1)};
+        // Each routine reads every source limb before it writes its first result limb, so a destination
+        // may alias a source.  For the in-place pair (d1,s1) = (d1+s1, d1-s1) the sum waits in registers
+        // until the difference has been formed from the untouched sources.
+        if (op == U_ADDSUB) {
+            uint32_t rs[NL];
+            mod_add_stream<NL>(A, B, P, [&](int k, uint32_t val) { rs[k] = val; });
+            uint32_t *dst2 = S.ptr(resolve((u >> 8) & 15u, permbits));
+            mod_sub_stream<NL>(A, B, P, [&](int k, uint32_t val) { dst2[k * STRIDE] = val; });
+            uint32_t *dst = S.ptr(d);
+#pragma unroll
+            for (int k = 0; k < NL; k++) dst[k * STRIDE] = rs[k];
+        } else if (op == U_ADD) {
+            uint32_t *dst = S.ptr(d);
+            mod_add_stream<NL>(A, B, P, [&](int k, uint32_t val) { dst[k * STRIDE] = val; });
+        } else {
+            uint32_t *dst = S.ptr(d);
+            mod_sub_stream<NL>(A, B, P, [&](int k, uint32_t val) { dst[k * STRIDE] = val; });
+        }
+    } else {  // U_COPY
+        const uint32_t *src = S.ptr(x);
+        uint32_t *dst = S.ptr(d);
+#pragma unroll 8
+        for (int k = 0; k < NL; k++) dst[k * STRIDE] = src[k * STRIDE];
+    }
+}
+
 // Execute one micro-op on the slot file.
 template <int NL, class SlotsT>
 __device__ __forceinline__ void exec_uop(const SlotsT &S, uint32_t u, uint32_t permbits,
@@ -139,6 +202,11 @@ __device__ __forceinline__ void exec_uop(const SlotsT &S, uint32_t u, uint32_t p
     const uint32_t d = resolve((u >> 4) & 15u, permbits);
     const uint32_t x = resolve((u >> 12) & 15u, permbits);
     const uint32_t y = resolve((u >> 16) & 15u, permbits);
+    if constexpr (NL > 32) {
+        // wide moduli: operands stay in shared memory and are streamed into the multiply
+        exec_uop_stream<NL>(S, u, op, d, x, y, permbits, P);
+        return;
+    }
     if (op == U_MUL2) {
         const uint32_t e = resolve((u >> 8) & 15u, permbits);
         const uint32_t x2 = resolve((u >> 20) & 15u, permbits);

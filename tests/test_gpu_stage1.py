@@ -76,3 +76,33 @@ def test_time_sliced_stage1_equals_one_shot():
     finally:
         ctx.close()
     assert a == b
+
+
+def test_error_behaviour_of_the_abi():
+    """Misuse returns an error code with a message instead of crashing (the reference exit(1)s)."""
+    N = composites()["syn415"]
+    ctx = E.EcmContext(N, 64)
+    try:
+        with pytest.raises(E.EcmError, match="no curves"):
+            ctx.stage1(1000)
+        with pytest.raises(E.EcmError, match="sigma must be >= 6"):
+            ctx.build_curves([5])
+        with pytest.raises(E.EcmError, match="exceeds"):
+            ctx.build_curves(list(range(10, 10 + 65)))
+        ctx.build_curves([7, 8, 9])
+        with pytest.raises(E.EcmError, match="B1 out of range"):
+            ctx.stage1(200000000)
+        with pytest.raises(E.EcmError, match="not been run"):
+            ctx.read_stage2()
+        ctx.stage1(1000)
+        with pytest.raises(E.EcmError, match="already run"):
+            ctx.stage1(1000)
+        with pytest.raises(E.EcmError, match="B2 must exceed B1"):
+            ctx.stage2(1000, 1000)
+        # a fresh batch on the same context works after the errors
+        ctx.build_curves([7, 8, 9]); ctx.stage1(1000)
+        x, z, _ = ctx.read_stage1()
+        o = O.ecm_curve(N, 1000, 1000, 8)
+        assert (x[1], z[1]) == (o["x"], o["z"])
+    finally:
+        ctx.close()
