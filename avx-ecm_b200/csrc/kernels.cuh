@@ -279,7 +279,7 @@ __global__ void k_fieldop(const ModParams<NL> P, const ModParams<NL> *Pg, int op
 // Table entry e of curve c: see tab_base().
 // =================================================================================================
 enum : uint32_t { V2_MUL = 0, V2_SQR = 1, V2_ADD = 2, V2_SUB = 3, V2_ADDSUB = 4, V2_COPY = 5, V2_LDG = 6, V2_STG = 7,
-                  V2_INV = 8, V2_ONE = 9, V2_PAIR = 10, V2_NOP = 11 };
+                  V2_INV = 8, V2_ONE = 9, V2_PAIR = 10, V2_NOP = 11, V2_MUL2 = 12 };
 enum : uint32_t { V2_SP = 10, V2_ACC = 11, NSLOT_S2 = 14 };
 
 // d = 1/x (both Montgomery form).  Non-invertible x: reproduce what lane 0 of the reference's
@@ -329,7 +329,25 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
         const uint64_t ins = __ldg(code + i);
         const uint32_t lo = (uint32_t)ins, imm = (uint32_t)(ins >> 32);
         const uint32_t op = lo & 0xffu, d = (lo >> 8) & 0xffu, x = (lo >> 16) & 0xffu, y = lo >> 24;
-        if (op == V2_SQR && UseSqr<NL>::value) {
+        if (op == V2_MUL2) {
+            const uint32_t d4 = (lo >> 8) & 15u, x4 = (lo >> 12) & 15u, y4 = (lo >> 16) & 15u;
+            const uint32_t e4 = (lo >> 20) & 15u, u4 = (lo >> 24) & 15u, v4 = lo >> 28;
+            if (NL <= 16) {
+                uint32_t a1[NL], b1[NL], r1[NL];
+                S.load(a, x4); S.load(b, y4); S.load(a1, u4); S.load(b1, v4);
+                mont_mul2<NL>(r, a, b, r1, a1, b1, P);
+                S.store(d4, r); S.store(e4, r1);
+            } else {
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t xs = h ? u4 : x4, ys = h ? v4 : y4;
+                    S.load(a, xs);
+                    if (xs == ys && UseSqr<NL>::value) mont_sqr<NL>(r, a, P);
+                    else { S.load(b, ys); mont_mul<NL>(r, a, b, P); }
+                    S.store(h ? e4 : d4, r);
+                }
+            }
+        } else if (op == V2_SQR && UseSqr<NL>::value) {
             S.load(a, x);
             mont_sqr<NL>(r, a, P);
             S.store(d, r);

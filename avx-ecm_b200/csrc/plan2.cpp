@@ -29,6 +29,11 @@ struct Asm {
     void inv(uint32_t d, uint32_t x) { put(V_INV, d, x, 0); }
     void one(uint32_t d) { put(V_ONE, d, 0, 0); }
     void pair(uint32_t e_pa, uint32_t e_pb) { put(V_PAIR, 0, 0, 0, e_pa | (e_pb << 16)); }
+    // d = x*y and e = u*v, independent (all four operands are read before either result is written)
+    void mul2(uint32_t d, uint32_t x, uint32_t y, uint32_t e, uint32_t u, uint32_t v)
+    {
+        code.push_back((uint64_t)(V_MUL2 | (d << 8) | (x << 12) | (y << 16) | (e << 20) | (u << 24) | (v << 28)));
+    }
     void ldpt(Pt p, uint32_t ex, uint32_t ez) { ldg(p.x, ex); ldg(p.z, ez); }
     void stpt(Pt p, uint32_t ex, uint32_t ez) { stg(p.x, ex); stg(p.z, ez); }
 
@@ -40,13 +45,10 @@ struct Asm {
     // leaves s2,d2 intact.  out must differ from in.
     void vadd(Pt in, Pt out)
     {
-        mul(D1_, D1_, S2_);
-        mul(S1_, S1_, D2_);
+        mul2(D1_, D1_, S2_, S1_, S1_, D2_);
         addsub(D1_, S1_, D1_, S1_);
-        sqr(D1_, D1_);
-        sqr(S1_, S1_);
-        mul(out.x, D1_, in.z);
-        mul(out.z, S1_, in.x);
+        mul2(D1_, D1_, D1_, S1_, S1_, S1_);
+        mul2(out.x, D1_, in.z, out.z, S1_, in.x);
     }
     // same operation with the roles of the two pairs exchanged (identical values: the only change
     // is the sign of the squared difference); clobbers s2,d2, leaves s1,d1 intact.
@@ -63,11 +65,9 @@ struct Asm {
     // vec_duplicate (ecm.c:445-457) from sums (s,d); tmp is any dead slot; clobbers s,d
     void vdup(uint32_t s, uint32_t d, uint32_t tmp, Pt out)
     {
-        sqr(d, d);
-        sqr(s, s);
-        mul(out.x, d, s);
+        mul2(d, d, d, s, s, s);
         sub(tmp, s, d);
-        mul(s, tmp, SP_);
+        mul2(out.x, d, s, s, tmp, SP_);
         add(s, s, d);
         mul(out.z, s, tmp);
     }
@@ -116,12 +116,11 @@ void batch_invert(Asm &a, const std::vector<uint32_t> &xs, const std::vector<uin
     a.inv(T1_, T1_);                               // B[n-1]
     for (size_t i = n - 1; i >= 1; i--) {
         a.ldg(T2_, pref + (uint32_t)i - 1);
-        a.mul(T2_, T1_, T2_);                      // 1/z[i] = B[i] * A[i-1]
+        a.ldg(D1_, zs[i]);
+        a.mul2(T2_, T1_, T2_, T1_, D1_, T1_);      // 1/z[i] = B[i] * A[i-1]   |   B[i-1] = z[i] * B[i]
         a.ldg(S1_, xs[i]);
         a.mul(S1_, S1_, T2_);
         a.stg(S1_, outs[i]);
-        a.ldg(T2_, zs[i]);
-        a.mul(T1_, T2_, T1_);                      // B[i-1] = z[i] * B[i]
     }
     a.ldg(S1_, xs[0]);
     a.mul(S1_, S1_, T1_);

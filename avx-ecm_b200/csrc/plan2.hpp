@@ -20,6 +20,7 @@ enum V2Op : uint32_t {
     V_ONE = 9,        // d = R mod N  (Montgomery 1)
     V_PAIR = 10,      // acc *= table[imm & 0xffff] - table[imm >> 16]      (CROSS_PRODUCT_INV, ecm.c:1857-1859)
     V_NOP = 11,
+    V_MUL2 = 12,      // two independent products: lo = op | d<<8 | x<<12 | y<<16 | e<<20 | u<<24 | v<<28 (4-bit slots)
 };
 // slot file of the stage-2 machine
 enum V2Slot : uint32_t {
