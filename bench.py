@@ -318,6 +318,22 @@ def main():
                 "products_per_sec": v2 * MODMUL_PER_CURVE * W2, "frac_of_imad_peak": v2 * MODMUL_PER_CURVE * W2 / peak_prod,
                 "composite": "syn1024", "curves": curves}
         c2.close()
+        # stage-2 sample on the bench composite: B1=1e5 -> B2=1e7 (D=2310, U=16), all curves of this GPU
+        sb1, sb2 = 100000, 10000000
+        ctx.build_curves(sig)
+        ctx.stage1(sb1)
+        t0 = time.time()
+        ctx.stage2(sb1, sb2)
+        s2_wall = time.time() - t0
+        s2_ms, s2_launches = ctx.last_timing()
+        cnt = ctx.stage2_counters()
+        table_bytes = (2 * cnt["s2_paired"]) * 4 * nl * curves          # Pa_inv + Pb operand of every pair step
+        also["stage2_sample"] = {"b1": sb1, "b2": sb2, "curves": curves, "device_s": s2_ms / 1e3, "wall_s": s2_wall,
+                                 "curves_per_sec": curves / (s2_ms / 1e3), "kernel_launches": s2_launches,
+                                 "pair_steps": cnt["s2_paired"], "point_adds": cnt["s2_ptadds"], "inversions": cnt["s2_numinv"],
+                                 "products_per_sec_adds_and_pairs": curves * (6 * cnt["s2_ptadds"] + cnt["s2_paired"]) * W / (s2_ms / 1e3),
+                                 "table_read_GBs_algorithmic": table_bytes / (s2_ms / 1e3) / 1e9,
+                                 "hbm_peak_GBs": 6540.8}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

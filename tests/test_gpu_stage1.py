@@ -106,3 +106,25 @@ def test_error_behaviour_of_the_abi():
         assert (x[1], z[1]) == (o["x"], o["z"])
     finally:
         ctx.close()
+
+
+def test_results_do_not_depend_on_block_size_or_schedule(monkeypatch):
+    """Size-independent property: the same batch run with different curve-group sizes (hence different
+    memory layouts, wave counts and launch schedules) must give identical residues for every curve."""
+    N = composites()["syn415"]
+    sig = list(range(500, 500 + 1500))
+    res = []
+    for threads in (None, "128", "320"):
+        if threads:
+            monkeypatch.setenv("ECM_B200_THREADS", threads)
+        else:
+            monkeypatch.delenv("ECM_B200_THREADS", raising=False)
+        ctx = E.EcmContext(N, len(sig))
+        try:
+            ctx.build_curves(sig); ctx.stage1(20000)
+            res.append(ctx.read_stage1())
+        finally:
+            ctx.close()
+    assert res[0] == res[1] == res[2]
+    o = O.ecm_curve(N, 20000, 20000, sig[1234])
+    assert (res[0][0][1234], res[0][1][1234]) == (o["x"], o["z"])
