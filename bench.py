@@ -352,7 +352,9 @@ def main():
                        "residue_check_vs_oracle": check},
             "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches,
             "roofline": {"bound": "imad", "achieved": prod_rate / 1e9, "peak": peak_all / 1e9, "unit": "Gprod/s",
-                         "frac": prod_rate / peak_all, "traffic": None,
+                         "frac": prod_rate / peak_all,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_final_stage1_ncu_full_summary.txt
+                         "traffic": 21007872,
                          "note": "achieved = curves/s x 12974547 modmul/curve x (2n^2+n) products, n=%d; peak = fastest of three live probes on this GPU "
                                  "(IMAD.WIDE.U32.X chains with uniform / per-thread multiplier, register-resident 32-limb Montgomery loop) "
                                  "at %.0f MHz; the pipe's arithmetic ceiling is 32 products/clk/SM" % (nl, peak_clk)},
