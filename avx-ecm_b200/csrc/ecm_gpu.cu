@@ -452,7 +452,7 @@ static int run_program(ecm_b200_ctx *c, const std::vector<uint64_t> &host_code, 
         if ((host_code[i] & 0xff) == V_PAIR) {
             uint64_t j = i;
             while (j < n && (host_code[j] & 0xff) == V_PAIR) j++;
-            if (j - i >= kMinRun) {
+            if (j - i >= kMinRun && c->eng->use_pair_kernel) {
                 int rc = run_vm2(c, d_code + seg, i - seg, state2, cap2, tab, groups, inv_fail);
                 if (rc) return rc;
                 {   // chunk-major (group, chunk) items, at most one resident wave per launch

@@ -29,6 +29,7 @@ struct Engine {
     virtual void vm2(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, uint32_t *tab, const uint64_t *code,
                      uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0, uint8_t *inv_fail) = 0;
     int threads_pair = 0, pair_blocks_per_sm = 1;
+    bool use_pair_kernel = true;                  // false for wide moduli: the pair steps run inside k_vm2
     virtual void pair_run(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, const uint32_t *tab, const uint64_t *code,
                           uint32_t npairs, uint32_t ncurves, uint32_t chunk_len, uint32_t groups, uint64_t item0) = 0;
     virtual void s2_setup(cudaStream_t st, const uint32_t *state1, Geom G1, uint32_t xslot, uint32_t zslot, uint32_t spslot,

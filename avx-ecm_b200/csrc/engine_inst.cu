@@ -16,7 +16,7 @@ struct EngineT : Engine {
     {
         nl = NL; stride_s1 = S1Cfg<NL>::STRIDE; smem_s1 = S1Cfg<NL>::smem;
         params_bytes = sizeof(ModParams<NL>);
-        threads_s2 = BlockCfg<NL, NSLOT_S2>::THREADS; smem_s2 = BlockCfg<NL, NSLOT_S2>::smem; nslot_s2 = NSLOT_S2;
+        threads_s2 = S2Cfg<NL>::THREADS; smem_s2 = S2Cfg<NL>::smem; nslot_s2 = NSLOT_S2;
     }
     void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, uint32_t m0inv) override
     {
@@ -30,7 +30,9 @@ struct EngineT : Engine {
         cudaError_t e = cudaFuncSetAttribute(k_stage1<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s1);
         if (e != cudaSuccess) return e;
         threads_pair = PairCfg<NL>::THREADS;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pair_blocks_per_sm, k_pair<NL>, threads_pair, 0);
+        use_pair_kernel = (NL <= 32);
+        if (!use_pair_kernel) return cudaFuncSetAttribute(k_vm2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
+        if constexpr (NL <= 32) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pair_blocks_per_sm, k_pair<NL>, threads_pair, 0);
         if (e != cudaSuccess) return e;
         if (pair_blocks_per_sm < 1) pair_blocks_per_sm = 1;
         return cudaFuncSetAttribute(k_vm2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
@@ -44,8 +46,10 @@ struct EngineT : Engine {
     void pair_run(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, const uint32_t *tab, const uint64_t *code,
                   uint32_t npairs, uint32_t ncurves, uint32_t chunk_len, uint32_t groups, uint64_t item0) override
     {
-        k_pair<NL><<<blocks, PairCfg<NL>::THREADS, 0, st>>>(P, state2, cap, tab, code, npairs, ncurves, chunk_len, groups, item0);
-        count_launch();
+        if constexpr (NL <= 32) {
+            k_pair<NL><<<blocks, PairCfg<NL>::THREADS, 0, st>>>(P, state2, cap, tab, code, npairs, ncurves, chunk_len, groups, item0);
+            count_launch();
+        }
     }
     void s2_setup(cudaStream_t st, const uint32_t *state1, Geom G1, uint32_t xslot, uint32_t zslot, uint32_t spslot,
                   uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab, uint32_t e_qx, uint32_t e_qz,

@@ -280,17 +280,17 @@ __global__ void k_fieldop(const ModParams<NL> P, const ModParams<NL> *Pg, int op
 // =================================================================================================
 enum : uint32_t { V2_MUL = 0, V2_SQR = 1, V2_ADD = 2, V2_SUB = 3, V2_ADDSUB = 4, V2_COPY = 5, V2_LDG = 6, V2_STG = 7,
                   V2_INV = 8, V2_ONE = 9, V2_PAIR = 10, V2_NOP = 11, V2_MUL2 = 12 };
-enum : uint32_t { V2_SP = 10, V2_ACC = 11, NSLOT_S2 = 14 };
+enum : uint32_t { V2_ACC = 6, V2_SP = 11, NSLOT_S2 = 14, NGLOBAL_S2 = 7 };   // slots 0..6 (points, acc) global, 7..13 shared
 
 // d = 1/x (both Montgomery form).  Non-invertible x: reproduce what lane 0 of the reference's
 // vectors does (ecm.c:1925-1949 with insert_mpz_to_vec main.c:117-138): the accumulator becomes the
 // raw gcd and the "inverse" is the raw, un-inverted product -- as Montgomery-domain values of the
 // reference (R_ref = 2^MAXBITS) these are g/R_ref and x/R_ref.
-template <int NL, int THREADS>
-__device__ __noinline__ void vm2_inverse(uint32_t *smem_thread, uint32_t d, uint32_t x, const ModParams<NL> *Pg, uint8_t *fail_flag)
+template <int NL, int STRIDE>
+__device__ __noinline__ void vm2_inverse(uint32_t *dptr, const uint32_t *xptr, uint32_t *accptr, const ModParams<NL> *Pg, uint8_t *fail_flag)
 {
     uint32_t a[NL], inv[NL], g[NL], t[NL];
-    for (int k = 0; k < NL; k++) a[k] = smem_thread[(x * NL + k) * THREADS];
+    for (int k = 0; k < NL; k++) a[k] = xptr[k * STRIDE];
     const bool ok = nm_inverse<NL>(inv, g, a, Pg);
     if (ok) {
         nm_mul<NL>(t, inv, Pg->r3, Pg);                   // (xR)^-1 * R^3 * R^-1 = x^-1 R
@@ -298,29 +298,51 @@ __device__ __noinline__ void vm2_inverse(uint32_t *smem_thread, uint32_t d, uint
         *fail_flag = 1;
         nm_mul<NL>(t, g, Pg->r2, Pg);                     // g in Montgomery form
         nm_mul<NL>(t, t, Pg->rrefinv, Pg);                // g / R_ref
-        for (int k = 0; k < NL; k++) smem_thread[(V2_ACC * NL + k) * THREADS] = t[k];
+        for (int k = 0; k < NL; k++) accptr[k * STRIDE] = t[k];
         nm_mul<NL>(t, a, Pg->rrefinv, Pg);                // x / R_ref
     }
-    for (int k = 0; k < NL; k++) smem_thread[(d * NL + k) * THREADS] = t[k];
+    for (int k = 0; k < NL; k++) dptr[k * STRIDE] = t[k];
 }
 
+// Block geometry of the stage-2 machine.  Up to 32 limbs the slot file is hybrid like stage 1's (the three
+// work points and the accumulator stay in the L2-resident state, 7 scratch slots in shared memory), which
+// doubles the resident warps at 1024 bits (128 -> 256 threads); wider moduli keep all 14 slots in shared.
 template <int NL>
-__global__ void __launch_bounds__(BlockCfg<NL, NSLOT_S2>::THREADS, 1)
+struct S2Cfg {
+    // measured: +21 % at 32 limbs (128 -> 256 threads per SM), -3 % at 13 limbs where 256 threads fit anyway
+    static constexpr bool HYBRID = (NL >= 20 && NL <= 32);
+    static constexpr int nsmem = HYBRID ? (NSLOT_S2 - NGLOBAL_S2) : NSLOT_S2;
+    static constexpr int per_thread = nsmem * NL * 4;
+    static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
+    static constexpr int even = fit >= 128 ? fit / 128 * 128 : fit;
+    static constexpr int cap = (NL <= 16) ? 384 : 256;           // register budget of the dual-product path
+    static constexpr int THREADS = even > cap ? cap : (even < 32 ? 32 : even);
+    static constexpr int smem = per_thread * THREADS;
+};
+
+template <int NL>
+__global__ void __launch_bounds__(S2Cfg<NL>::THREADS, 1)
 k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ state2, uint32_t cap, uint32_t *__restrict__ tab,
       const uint64_t *__restrict__ code, uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0,
       uint8_t *__restrict__ inv_fail)
 {
-    constexpr int THREADS = BlockCfg<NL, NSLOT_S2>::THREADS;
+    constexpr int THREADS = S2Cfg<NL>::THREADS;
+    constexpr int NG = S2Cfg<NL>::HYBRID ? NGLOBAL_S2 : 0;          // slots served from the global state
     extern __shared__ uint32_t smem[];
     const uint64_t item = item0 + blockIdx.x;
     const uint32_t g = (uint32_t)(item % groups);
     const uint64_t chunk = item / groups;
     const uint32_t curve = g * THREADS + threadIdx.x;
     const uint32_t nwg = cap >> 5;
-    Slots<NL, THREADS> S{smem + threadIdx.x};
+    // state2 is group-blocked: [group][slot][limb][THREADS]
+    HybridSlots<NL, THREADS, NG, NSLOT_S2 - NG> S{state2 + (size_t)g * (NSLOT_S2 * NL * THREADS) + threadIdx.x, smem + threadIdx.x};
     uint32_t a[NL], b[NL], r[NL];
 #pragma unroll 1
-    for (uint32_t s = 0; s < NSLOT_S2; s++) { gload<NL>(r, state2, cap, s, curve); S.store(s, r); }
+    for (uint32_t s = NG; s < NSLOT_S2; s++) {
+#pragma unroll
+        for (int k = 0; k < NL; k++) r[k] = S.gl[(s * NL + k) * THREADS];
+        S.store(s, r);
+    }
 
     uint64_t i = chunk * chunk_len;
     const uint64_t end = (i + chunk_len < ncode) ? i + chunk_len : ncode;
@@ -381,7 +403,7 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
         } else if (op == V2_STG) {
             S.load(a, x); tstore<NL>(tab, tab_base(imm, nwg, curve, NL), a);
         } else if (op == V2_INV) {
-            vm2_inverse<NL, THREADS>(smem + threadIdx.x, d, x, Pg, inv_fail + curve);
+            vm2_inverse<NL, THREADS>(S.ptr(d), S.ptr(x), S.ptr(V2_ACC), Pg, inv_fail + curve);
         } else if (op == V2_ONE) {
 #pragma unroll
             for (int k = 0; k < NL; k++) a[k] = P.one[k];
@@ -389,7 +411,11 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
         }
     }
 #pragma unroll 1
-    for (uint32_t s = 0; s < NSLOT_S2; s++) { S.load(r, s); gstore<NL>(state2, cap, s, curve, r); }
+    for (uint32_t s = NG; s < NSLOT_S2; s++) {
+        S.load(r, s);
+#pragma unroll
+        for (int k = 0; k < NL; k++) S.gl[(s * NL + k) * THREADS] = r[k];
+    }
 }
 
 // ---- the pair loop as its own kernel ----------------------------------------------------------------
@@ -414,6 +440,7 @@ __global__ void __launch_bounds__(PairCfg<NL>::THREADS)
 k_pair(const ModParams<NL> P, uint32_t *__restrict__ state2, uint32_t cap, const uint32_t *__restrict__ tab,
        const uint64_t *__restrict__ code, uint32_t npairs, uint32_t ncurves, uint32_t chunk_len, uint32_t groups, uint64_t item0)
 {
+    constexpr int T2 = S2Cfg<NL>::THREADS;                        // group size of the state2 layout
     const uint64_t item = item0 + blockIdx.x;
     const uint32_t g = (uint32_t)(item % groups);
     const uint32_t chunk = (uint32_t)(item / groups);
@@ -424,7 +451,9 @@ k_pair(const ModParams<NL> P, uint32_t *__restrict__ state2, uint32_t cap, const
     const uint32_t nwg = cap >> 5;
     if (PairCfg<NL>::DUAL) {
         uint32_t acc0[NL], acc1[NL], t0[NL], t1[NL], v[NL];
-        gload<NL>(acc0, state2, cap, V2_ACC, curve);
+        uint32_t *accp = state2 + ((size_t)(curve / T2) * NSLOT_S2 + V2_ACC) * (NL * T2) + (curve % T2);
+#pragma unroll
+        for (int k = 0; k < NL; k++) acc0[k] = accp[k * T2];
 #pragma unroll
         for (int k = 0; k < NL; k++) acc1[k] = P.one[k];
 #pragma unroll 1
@@ -445,10 +474,13 @@ k_pair(const ModParams<NL> P, uint32_t *__restrict__ state2, uint32_t cap, const
             mont_mul2<NL>(acc0, acc0, t0, acc1, acc1, t1, P);
         }
         mont_mul<NL>(acc0, acc0, acc1, P);
-        gstore<NL>(state2, cap, V2_ACC, curve, acc0);
+#pragma unroll
+        for (int k = 0; k < NL; k++) accp[k * T2] = acc0[k];
     } else {
         uint32_t acc[NL], u[NL], v[NL];
-        gload<NL>(acc, state2, cap, V2_ACC, curve);
+        uint32_t *accp = state2 + ((size_t)(curve / T2) * NSLOT_S2 + V2_ACC) * (NL * T2) + (curve % T2);
+#pragma unroll
+        for (int k = 0; k < NL; k++) acc[k] = accp[k * T2];
 #pragma unroll 1
         for (; i < end; i++) {
             const uint32_t imm = (uint32_t)(__ldg(code + i) >> 32);
@@ -457,7 +489,8 @@ k_pair(const ModParams<NL> P, uint32_t *__restrict__ state2, uint32_t cap, const
             mod_sub<NL>(u, u, v, P);
             mont_mul<NL>(acc, acc, u, P);
         }
-        gstore<NL>(state2, cap, V2_ACC, curve, acc);
+#pragma unroll
+        for (int k = 0; k < NL; k++) accp[k * T2] = acc[k];
     }
 }
 
@@ -469,6 +502,7 @@ __global__ void k_s2_setup(const uint32_t *state1, Geom G1, uint32_t xslot, uint
                            uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab,
                            uint32_t e_qx, uint32_t e_qz, uint8_t *inv_fail)
 {
+    const Geom G2{(uint32_t)S2Cfg<NL>::THREADS, (uint32_t)S2Cfg<NL>::THREADS, NSLOT_S2};
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cap2) return;
     uint32_t src = first + c; if (src >= count) src = count - 1;
@@ -476,7 +510,7 @@ __global__ void k_s2_setup(const uint32_t *state1, Geom G1, uint32_t xslot, uint
         tab[tab_base(e_qx, cap2 >> 5, c, NL) + (size_t)k * 32] = state1[G1.idx(src, xslot, k, NL)];
         tab[tab_base(e_qz, cap2 >> 5, c, NL) + (size_t)k * 32] = state1[G1.idx(src, zslot, k, NL)];
         for (uint32_t s = 0; s < NSLOT_S2; s++)
-            state2[((size_t)s * NL + k) * cap2 + c] = (s == V2_SP) ? state1[G1.idx(src, spslot, k, NL)] : 0;
+            state2[G2.idx(c, s, k, NL)] = (s == V2_SP) ? state1[G1.idx(src, spslot, k, NL)] : 0;
     }
     inv_fail[c] = 0;
 }
@@ -487,7 +521,8 @@ __global__ void k_s2_collect(const uint32_t *state2, uint32_t cap2, const uint8_
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
-    for (int k = 0; k < NL; k++) acc_out[(size_t)k * count + first + c] = state2[((size_t)V2_ACC * NL + k) * cap2 + c];
+    const Geom G2{(uint32_t)S2Cfg<NL>::THREADS, (uint32_t)S2Cfg<NL>::THREADS, NSLOT_S2};
+    for (int k = 0; k < NL; k++) acc_out[(size_t)k * count + first + c] = state2[G2.idx(c, V2_ACC, k, NL)];
     fail_out[first + c] = inv_fail[c];
 }
 

@@ -24,10 +24,10 @@ enum V2Op : uint32_t {
 };
 // slot file of the stage-2 machine
 enum V2Slot : uint32_t {
-    UX = 0, UZ, VX, VZ, WX, WZ,        // three work points
-    S1_ = 6, D1_, S2_, D2_,            // sums / differences
-    SP_ = 10,                          // (A+2)/4
-    ACC = 11,                          // stage-2 accumulator
+    UX = 0, UZ, VX, VZ, WX, WZ,        // three work points            } kept in global memory (L2) by the
+    ACC = 6,                           // stage-2 accumulator           } hybrid slot file of k_vm2
+    S1_ = 7, D1_, S2_, D2_,            // sums / differences            } shared memory
+    SP_ = 11,                          // (A+2)/4
     T1_ = 12, T2_ = 13,
     NSLOT_S2 = 14
 };

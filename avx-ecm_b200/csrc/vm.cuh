@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t resolve(uint32_t sym, uint32_t permbits)
 // shared memory.  A multiply takes thousands of cycles, so the L2 latency of the point reads is
 // hidden by the other resident warps, and the small shared footprint (5 slots) is what lets 14-16
 // warps share an SM instead of 10.
-template <int NL, int STRIDE>
+template <int NL, int STRIDE, int NGLOBAL = 8, int NSMEM = 5>
 struct HybridSlots {
     uint32_t *gl;     // state of this block's group + threadIdx.x
     uint32_t *sm;     // smem + threadIdx.x
@@ -108,12 +108,12 @@ struct HybridSlots {
     // one of two shared staging slots (shared indices 5 and 6)
     __device__ __forceinline__ uint32_t *ptr(uint32_t slot) const
     {
-        return slot < 8 ? gl + slot * (NL * STRIDE) : sm + (slot - 8) * (NL * STRIDE);
+        return slot < NGLOBAL ? gl + slot * (NL * STRIDE) : sm + (slot - NGLOBAL) * (NL * STRIDE);
     }
     __device__ __forceinline__ const uint32_t *operand(uint32_t slot, int staging) const
     {
-        if (slot >= 8) return sm + (slot - 8) * (NL * STRIDE);
-        uint32_t *dst = sm + (5 + staging) * (NL * STRIDE);
+        if (slot >= NGLOBAL) return sm + (slot - NGLOBAL) * (NL * STRIDE);
+        uint32_t *dst = sm + (NSMEM + staging) * (NL * STRIDE);
         const uint32_t *src = gl + slot * (NL * STRIDE);
 #pragma unroll 8
         for (int k = 0; k < NL; k++) dst[k * STRIDE] = src[k * STRIDE];
@@ -121,24 +121,24 @@ struct HybridSlots {
     }
     __device__ __forceinline__ void load(uint32_t (&r)[NL], uint32_t slot) const
     {
-        if (slot < 8) {
+        if (slot < NGLOBAL) {
             const uint32_t *p = gl + slot * (NL * STRIDE);
 #pragma unroll
             for (int k = 0; k < NL; k++) r[k] = p[k * STRIDE];
         } else {
-            const uint32_t *p = sm + (slot - 8) * (NL * STRIDE);
+            const uint32_t *p = sm + (slot - NGLOBAL) * (NL * STRIDE);
 #pragma unroll
             for (int k = 0; k < NL; k++) r[k] = p[k * STRIDE];
         }
     }
     __device__ __forceinline__ void store(uint32_t slot, const uint32_t (&r)[NL]) const
     {
-        if (slot < 8) {
+        if (slot < NGLOBAL) {
             uint32_t *p = gl + slot * (NL * STRIDE);
 #pragma unroll
             for (int k = 0; k < NL; k++) p[k * STRIDE] = r[k];
         } else {
-            uint32_t *p = sm + (slot - 8) * (NL * STRIDE);
+            uint32_t *p = sm + (slot - NGLOBAL) * (NL * STRIDE);
 #pragma unroll
             for (int k = 0; k < NL; k++) p[k * STRIDE] = r[k];
         }
