@@ -450,27 +450,28 @@ k_pair(const ModParams<NL> P, uint32_t *__restrict__ state2, uint32_t cap, const
     const uint32_t end = (i + chunk_len < npairs) ? i + chunk_len : npairs;
     const uint32_t nwg = cap >> 5;
     if (PairCfg<NL>::DUAL) {
-        uint32_t acc0[NL], acc1[NL], t0[NL], t1[NL], v[NL];
+        // software pipeline: the table operands of steps i+2, i+3 are in flight while steps i, i+1 multiply
+        uint32_t acc0[NL], acc1[NL], t0[NL], t1[NL], pu0[NL], pv0[NL], pu1[NL], pv1[NL];
         uint32_t *accp = state2 + ((size_t)(curve / T2) * NSLOT_S2 + V2_ACC) * (NL * T2) + (curve % T2);
 #pragma unroll
-        for (int k = 0; k < NL; k++) acc0[k] = accp[k * T2];
-#pragma unroll
-        for (int k = 0; k < NL; k++) acc1[k] = P.one[k];
+        for (int k = 0; k < NL; k++) { acc0[k] = accp[k * T2]; acc1[k] = P.one[k]; }
+        auto fetch = [&](uint32_t j, uint32_t (&pu)[NL], uint32_t (&pv)[NL]) {
+            const uint32_t imm = (uint32_t)(__ldg(code + j) >> 32);
+            tload<NL>(pu, tab, tab_base(imm & 0xffffu, nwg, curve, NL));
+            tload<NL>(pv, tab, tab_base(imm >> 16, nwg, curve, NL));
+        };
+        if (i < end) fetch(i, pu0, pv0);
+        if (i + 1 < end) fetch(i + 1, pu1, pv1);
 #pragma unroll 1
         for (; i < end; i += 2) {
-            const uint32_t imm0 = (uint32_t)(__ldg(code + i) >> 32);
-            tload<NL>(t0, tab, tab_base(imm0 & 0xffffu, nwg, curve, NL));
-            tload<NL>(v, tab, tab_base(imm0 >> 16, nwg, curve, NL));
-            mod_sub<NL>(t0, t0, v, P);
-            if (i + 1 < end) {
-                const uint32_t imm1 = (uint32_t)(__ldg(code + i + 1) >> 32);
-                tload<NL>(t1, tab, tab_base(imm1 & 0xffffu, nwg, curve, NL));
-                tload<NL>(v, tab, tab_base(imm1 >> 16, nwg, curve, NL));
-                mod_sub<NL>(t1, t1, v, P);
-            } else {
+            mod_sub<NL>(t0, pu0, pv0, P);
+            if (i + 1 < end) mod_sub<NL>(t1, pu1, pv1, P);
+            else {
 #pragma unroll
                 for (int k = 0; k < NL; k++) t1[k] = P.one[k];
             }
+            if (i + 2 < end) fetch(i + 2, pu0, pv0);
+            if (i + 3 < end) fetch(i + 3, pu1, pv1);
             mont_mul2<NL>(acc0, acc0, t0, acc1, acc1, t1, P);
         }
         mont_mul<NL>(acc0, acc0, acc1, P);

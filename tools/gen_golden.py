@@ -79,6 +79,7 @@ def composites():
         "csh250k": 171527316193270871507108435893460246746982712299171622350010323023149618461701108180621787596877308885636902619030669,
         "csh1m": 7908926676514675413083853032827063880118980193445471625562601469958414706043143581401715516956542424923236530406833110566233,
         "small96": 1000000007 * 998244353 * 4294967311,   # tiny composite: exercises factor/inversion-failure paths
+        "csh150m": 19223719229397103735869895564468606263251785680561653388554202432164204897138631706690937388406707574740021324772129,
     }
 
 
@@ -102,6 +103,7 @@ def cases():
         ("small96_D60", c["small96"], 8, 100, 10000, 11),
         ("small96_D30", c["small96"], 8, 50, 5000, 11),
         ("syn415_two_ranges", c["syn415"], 8, 2000, 100100000, 7),   # B2 spans two 1e8 prime ranges
+        ("csh150m_b1_1e6_two_ranges", c["csh150m"], 8, 1000000, 150000000, 3018506502),   # test.csh line 6
     ]
 
 
