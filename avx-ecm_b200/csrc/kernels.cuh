@@ -13,28 +13,6 @@ namespace ecmb200 {
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int NSMEM_S1 = 5;      // stage-1 slots kept in shared memory (s1,d1,s2,d2,sp); the 8 point slots stay in global
 
-template <int NL, int NSLOT>
-struct BlockCfg {
-    static constexpr int per_thread = NSLOT * NL * 4;
-    static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
-    // whole multiples of 4 warps keep the four sub-partitions evenly loaded
-    static constexpr int even = fit >= 128 ? fit / 128 * 128 : fit;
-    static constexpr int THREADS = even > 512 ? 512 : (even < 32 ? 32 : even);
-    static constexpr int smem = per_thread * THREADS;
-};
-
-template <int NL>
-__device__ __forceinline__ void gload(uint32_t (&r)[NL], const uint32_t *state, uint32_t cap, uint32_t slot, uint32_t curve)
-{
-#pragma unroll
-    for (int k = 0; k < NL; k++) r[k] = state[((size_t)slot * NL + k) * cap + curve];
-}
-template <int NL>
-__device__ __forceinline__ void gstore(uint32_t *state, uint32_t cap, uint32_t slot, uint32_t curve, const uint32_t (&r)[NL])
-{
-#pragma unroll
-    for (int k = 0; k < NL; k++) state[((size_t)slot * NL + k) * cap + curve] = r[k];
-}
 
 // Stage-2 tables: entry e of curve c lives at tab[((e*nwg + c/32)*NL + limb)*32 + c%32]: the NL limbs of a
 // warp's 32 curves form one contiguous NL*128-byte block, so an operand costs one 64-bit address

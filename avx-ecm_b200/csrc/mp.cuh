@@ -444,14 +444,4 @@ __device__ __forceinline__ void mod_sub_stream(const AT &a, const BT &b, const M
     for (int k = 1; k < NL; k++) { v = (k == NL - 1) ? addc3(t[k], P.n[k] & bo) : addc3_cc(t[k], P.n[k] & bo); put(k, v); }
 }
 
-// 1 if a == 0
-template <int NL>
-__device__ __forceinline__ bool is_zero(const uint32_t (&a)[NL])
-{
-    uint32_t o = 0;
-#pragma unroll
-    for (int k = 0; k < NL; k++) o |= a[k];
-    return o == 0;
-}
-
 }  // namespace ecmb200

@@ -50,18 +50,6 @@ struct Asm {
         mul2(D1_, D1_, D1_, S1_, S1_, S1_);
         mul2(out.x, D1_, in.z, out.z, S1_, in.x);
     }
-    // same operation with the roles of the two pairs exchanged (identical values: the only change
-    // is the sign of the squared difference); clobbers s2,d2, leaves s1,d1 intact.
-    void vadd_swapped(Pt in, Pt out)
-    {
-        mul(D2_, D2_, S1_);
-        mul(S2_, S2_, D1_);
-        addsub(D2_, S2_, D2_, S2_);
-        sqr(D2_, D2_);
-        sqr(S2_, S2_);
-        mul(out.x, D2_, in.z);
-        mul(out.z, S2_, in.x);
-    }
     // vec_duplicate (ecm.c:445-457) from sums (s,d); tmp is any dead slot; clobbers s,d
     void vdup(uint32_t s, uint32_t d, uint32_t tmp, Pt out)
     {

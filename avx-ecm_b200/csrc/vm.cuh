@@ -4,9 +4,10 @@
 // chain for a prime does not depend on the curve), so the host compiles stage 1 / stage 2 into
 // a compact stream of macro-ops once and every thread of the grid interprets it with zero
 // divergence.  A macro-op expands (from a table in constant memory) into field micro-ops on
-// numbered slots; slots live in shared memory as [slot][limb][thread] (bank = thread, conflict
-// free), operands are pulled into registers for the multiply.  Only ONE copy of the unrolled
-// Montgomery multiply exists in the kernel, which keeps the instruction footprint small.
+// numbered slots (HybridSlots below: points in the L2-resident global state, hot scratch values in
+// shared memory as [slot][limb][thread], bank = thread, conflict free); operands are pulled into
+// registers for the multiply.  One copy each of the unrolled single and dual Montgomery multiply
+// exists in the kernel, which keeps the instruction footprint small.
 //
 // Reference semantics reproduced (Appendix A of SURVEY.md):
 //   vec_add        ecm.c:407-443      vec_duplicate  ecm.c:445-457
@@ -70,24 +71,6 @@ static __constant__ uint32_t c_prog_s1[8][MAXPROG] = {
 static __constant__ uint8_t c_perm[24] = {
     0xE4, 0xB4, 0xD8, 0x78, 0x9C, 0x6C, 0xE1, 0xB1, 0xC9, 0x39, 0x8D, 0x2D,
     0xD2, 0x72, 0xC6, 0x36, 0x4E, 0x1E, 0x93, 0x63, 0x87, 0x27, 0x4B, 0x1B };
-
-// ---- slot access: [slot][limb][thread] in shared memory ------------------------------------
-template <int NL, int THREADS>
-struct Slots {
-    uint32_t *base;   // smem + threadIdx.x
-    __device__ __forceinline__ void load(uint32_t (&r)[NL], uint32_t slot) const
-    {
-        const uint32_t *p = base + slot * (NL * THREADS);
-#pragma unroll
-        for (int k = 0; k < NL; k++) r[k] = p[k * THREADS];
-    }
-    __device__ __forceinline__ void store(uint32_t slot, const uint32_t (&r)[NL]) const
-    {
-        uint32_t *p = base + slot * (NL * THREADS);
-#pragma unroll
-        for (int k = 0; k < NL; k++) p[k * THREADS] = r[k];
-    }
-};
 
 __device__ __forceinline__ uint32_t resolve(uint32_t sym, uint32_t permbits)
 {
