@@ -169,6 +169,14 @@ int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimb
     {
         const uint32_t S = (uint32_t)eng->stride_s1, sms = (uint32_t)c->num_sms;
         uint32_t bestT = 0; double best = 0;
+        // small batches: 1-2 warps per block spread over more SMs finish sooner than a few full blocks
+        for (uint32_t T : {32u, 64u}) {
+            if (T > S) break;
+            const uint32_t gr = (max_curves + T - 1) / T;
+            const double w = T / 32.0;
+            const double score = (double)std::min(gr, sms) / sms * (w / (w + 3.6)) * ((double)max_curves / ((double)gr * T));
+            if (score > best) { best = score; bestT = T; }
+        }
         for (uint32_t T = 128; T <= S; T += 128) {
             const uint32_t gr = (max_curves + T - 1) / T;
             const double w = T / 32.0;
@@ -518,6 +526,10 @@ int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
     const size_t budget = (size_t)((double)free_b * 0.90) - std::min<size_t>(code_bytes + (64u << 20), free_b / 4);
     uint32_t cap2 = (uint32_t)std::min<size_t>((c->count + T - 1) / T * T, budget / per_curve / T * T);
     if (cap2 < T) return fail(ECM_B200_ENOMEM, "not enough device memory for one stage-2 group");
+    if (const char *e = getenv("ECM_B200_S2_WAVE")) {        // test hook: force small waves
+        const uint32_t w = ((uint32_t)atoi(e) + T - 1) / T * T;
+        if (w >= T && w < cap2) cap2 = w;
+    }
     {   // several waves: make them equal instead of one full wave plus a small remainder
         const uint32_t waves = (c->count + cap2 - 1) / cap2;
         const uint32_t even = ((c->count + waves - 1) / waves + T - 1) / T * T;

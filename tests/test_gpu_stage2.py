@@ -87,3 +87,20 @@ def test_cli_writes_reference_files(tmp_path):
         for m in re.finditer(r"found \S+ factor (\d+) in stage (\d) .*sigma (\d+)", res):
             got.add((m.group(3), int(m.group(2)), m.group(1)))
         assert got == {(f["sigma"], f["stage"], f["factor"]) for f in g["factors"]}
+
+
+def test_stage2_in_several_waves_equals_one_wave(monkeypatch):
+    """When the stage-2 tables of a batch do not fit in HBM the batch is processed in waves (1024-bit,
+    65 536 curves needs two).  Force small waves and compare with the single-wave result and the oracle."""
+    N = composites()["syn415"]
+    count, b1, b2 = 900, 1500, 40000
+    one = E.vececm(N, count, b1, b2, sigma=77)
+    monkeypatch.setenv("ECM_B200_S2_WAVE", "300")
+    ctx = E.EcmContext(N, count)
+    try:
+        many = E.vececm(N, count, b1, b2, sigma=77, ctx=ctx)
+    finally:
+        ctx.close()
+    assert many["acc"] == one["acc"] and many["factors"] == one["factors"] and many["inv_fail"] == one["inv_fail"]
+    for i in (0, 299, 300, 511, 899):
+        assert many["acc"][i] == O.ecm_curve(N, b1, b2, 77 + i)["acc"]
