@@ -304,12 +304,18 @@ int ecm_b200_stage1_begin(ecm_b200_ctx *c, uint64_t b1)
     c->launches_issued = 0;
     c->last_launches = 0;
     CU(cudaEventRecord(c->ev0, c->stream));
+    if (c->total_items == 0) {                    // nothing to do (B1 = 2): the point is unchanged
+        c->stage1_done = true;
+        c->p_slot = c->plan.final_slot;
+        CU(cudaEventRecord(c->ev1, c->stream));
+    }
     return ECM_B200_OK;
 }
 
 int ecm_b200_stage1_step(ecm_b200_ctx *c, uint32_t max_launches, int *done)
 {
     if (!c) return fail(ECM_B200_EINVAL, "null context");
+    if (c->total_items == 0 && c->stage1_done) { if (done) *done = 1; return ECM_B200_OK; }   // empty op stream (B1 = 2)
     if (c->total_items == 0) return fail(ECM_B200_ESTATE, "stage1_begin not called");
     CU(cudaSetDevice(c->device));
     const uint32_t per = std::min<uint32_t>(c->groups, (uint32_t)c->num_sms);

@@ -128,3 +128,18 @@ def test_results_do_not_depend_on_block_size_or_schedule(monkeypatch):
     assert res[0] == res[1] == res[2]
     o = O.ecm_curve(N, 20000, 20000, sig[1234])
     assert (res[0][0][1234], res[0][1][1234]) == (o["x"], o["z"])
+
+
+@pytest.mark.parametrize("b1", [2, 3, 4, 5, 6, 10])
+def test_tiny_b1_edge_cases(b1):
+    # B1 = 2 has an empty op stream, 3..4 only the power-of-two doublings (ecm.c:1815-1832)
+    N = composites()["syn415"]
+    ctx = E.EcmContext(N, 4)
+    try:
+        ctx.build_curves([7, 8, 9, 10]); ctx.stage1(b1)
+        x, z, _ = ctx.read_stage1()
+    finally:
+        ctx.close()
+    for i in range(4):
+        o = O.ecm_curve(N, b1, b1, 7 + i)
+        assert (x[i], z[i]) == (o["x"], o["z"])
