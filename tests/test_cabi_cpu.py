@@ -128,3 +128,17 @@ def test_cli_expression_evaluator_matches_python(expr, value):
     import subprocess
     out = subprocess.run([CLI, "--eval", expr], capture_output=True, text=True, check=True).stdout.strip()
     assert int(out) == value
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ecm_b200.h compiles as C99 and a C client links against the library (examples/abi_check.c);
+    without a GPU the client must see the engine refuse to run (no CPU fallback)."""
+    import subprocess
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.join(ROOT, "avx-ecm_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "abi_check.c"), "-o", exe, "-L", libdir, "-lecm_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "1980817 point-adds" in r.stdout and "D=2310 U=16 L=32 R=963" in r.stdout

@@ -104,3 +104,23 @@ def test_stage2_in_several_waves_equals_one_wave(monkeypatch):
     assert many["acc"] == one["acc"] and many["factors"] == one["factors"] and many["inv_fail"] == one["inv_fail"]
     for i in (0, 299, 300, 511, 899):
         assert many["acc"][i] == O.ecm_curve(N, b1, b2, 77 + i)["acc"]
+
+
+def test_plain_c_client_runs_both_stages(tmp_path):
+    """examples/abi_check.c (C99, no Python, no torch) drives stage 1 + stage 2 through the C ABI:
+    N = (2^89-1)(2^107-1), B1 = 2e4, B2 = 2e6 must expose the factor 2^89-1 for some sigma."""
+    import os, subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.join(ROOT, "avx-ecm_b200")
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "abi_check.c"),
+                    "-o", exe, "-L", libdir, "-lecm_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    N = (2 ** 89 - 1) * (2 ** 107 - 1)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("sigma")]
+    assert len(lines) == 8
+    for i, l in enumerate(lines):
+        o = O.ecm_curve(N, 20000, 2000000, 1000 + i)
+        got = int(l.split("0x")[1], 16) if "factor 0x" in l else 0
+        assert got == o["f2"], l
