@@ -64,6 +64,7 @@ def lib():
         "ecm_b200_stage2_counters": (c.c_int, [vp, u64p, u64p, u64p, u64p]),
         "ecm_b200_plan_stage1": (c.c_uint64, [c.c_uint64, u8p, c.c_uint64, u64p]),
         "ecm_b200_plan_stage2": (c.c_uint64, [c.c_uint64, c.c_uint64, u64p]),
+        "ecm_b200_stage2_program": (c.c_uint64, [c.c_uint64, c.c_uint64, c.c_int, u64p, c.c_uint64, u32p]),
         "ecm_b200_pair": (c.c_uint32, [c.c_uint64, c.c_uint64, c.c_uint32, c.c_uint32, u32p, u32p, c.c_uint32, u32p, u32p]),
         "ecm_b200_stage2_params": (None, [c.c_uint64, u32p, u32p, u32p, u32p]),
         "ecm_b200_fieldop": (c.c_int, [vp, c.c_int, c.c_uint32, u32p, u32p, u32p, c.c_int]),
@@ -81,7 +82,7 @@ def lib():
 EXPORTS = ["ecm_b200_create", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
            "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
            "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_stage1_progress", "ecm_b200_flush_l2", "ecm_b200_timer", "ecm_b200_read_stage1", "ecm_b200_stage2",
-           "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_pair", "ecm_b200_stage2_params",
+           "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_stage2_program", "ecm_b200_pair", "ecm_b200_stage2_params",
            "ecm_b200_fieldop", "ecm_b200_launch_count", "ecm_b200_last_timing", "ecm_b200_measure_imad_peak"]
 
 
@@ -258,6 +259,17 @@ def plan_stage2(b1, b2):
     n = lib().ecm_b200_plan_stage2(b1, b2, cnt)
     return {"instructions": n, "s2_ptadds": cnt[0], "s2_numinv": cnt[1], "s2_paired": cnt[2], "pairmap_steps": cnt[3],
             "last_amin": cnt[4], "table_entries": cnt[5]}
+
+
+def stage2_program(b1, b2, which):
+    """-> (list of 64-bit instruction words, layout dict) of the compiled stage-2 program (which = -1: init)."""
+    L = lib()
+    lay = (ctypes.c_uint32 * 13)()
+    n = L.ecm_b200_stage2_program(b1, b2, which, None, 0, lay)
+    buf = (ctypes.c_uint64 * max(1, n))()
+    L.ecm_b200_stage2_program(b1, b2, which, buf, n, lay)
+    names = ("npb", "pbx", "pbz", "pba", "pax", "paz", "pai", "paa", "qx", "qz", "pdx", "pdz", "entries")
+    return list(buf[:n]), dict(zip(names, lay))
 
 
 def pair(lo, hi, D, U=16):

@@ -660,6 +660,27 @@ uint64_t ecm_b200_plan_stage2(uint64_t b1, uint64_t b2, uint64_t *counts)
     return n;
 }
 
+uint64_t ecm_b200_stage2_program(uint64_t b1, uint64_t b2, int which, uint64_t *out, uint64_t cap, uint32_t *layout)
+{
+    Stage2Program pg;
+    plan_stage2_init(b1, pg);
+    const std::vector<uint64_t> *src = &pg.init;
+    if (which >= 0) {
+        uint64_t p = b1 + (uint64_t)which * 100000000ull;
+        if (p >= b2) return 0;
+        plan_stage2_range(p, std::min<uint64_t>(p + 100000000ull, b2), pg);
+        src = &pg.ranges.back();
+    }
+    if (out && cap >= src->size()) memcpy(out, src->data(), src->size() * 8);
+    if (layout) {
+        const Stage2Layout &L = pg.lay;
+        const uint32_t v[12] = {L.npb, L.pbx, L.pbz, L.pba, L.pax, L.paz, L.pai, L.paa, L.qx, L.qz, L.pdx, L.pdz};
+        memcpy(layout, v, sizeof v);
+        layout[12] = L.entries;
+    }
+    return src->size();
+}
+
 void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R)
 {
     Stage2Params p = stage2_params(b1);

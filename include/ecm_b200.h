@@ -100,6 +100,12 @@ uint32_t ecm_b200_pair(uint64_t lo, uint64_t hi, uint32_t D, uint32_t U, uint32_
  * counts[0..5] = point additions, inversions, pair products, pairmap steps (ecm.c:1481-1483),
  * final amin, table entries per curve.                                                         */
 uint64_t ecm_b200_plan_stage2(uint64_t b1, uint64_t b2, uint64_t *counts);
+/* The compiled stage-2 instruction stream itself (for inspection and for CPU-side checking of the
+ * compiler): which = -1 the ecm_stage2_init program, which = r >= 0 the program of the r-th 1e8 prime
+ * range.  Instruction word: lo = op | d<<8 | x<<16 | y<<24 (V_MUL2: 4-bit fields d,x,y,e,u,v from bit 8),
+ * hi = imm; op codes and slot numbers are listed in avx-ecm_b200/csrc/plan2.hpp.  layout[0..12] = npb,
+ * table bases pbx, pbz, pba, pax, paz, pai, paa, qx, qz, pdx, pdz, total entries.  Returns the length. */
+uint64_t ecm_b200_stage2_program(uint64_t b1, uint64_t b2, int which, uint64_t *out, uint64_t cap, uint32_t *layout);
 /* Stage-2 geometry chosen for B1 (thread_init, main.c:834-970): D, U, L, R.                    */
 void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R);
 

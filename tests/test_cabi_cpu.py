@@ -142,3 +142,20 @@ def test_header_is_plain_c_and_links(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "1980817 point-adds" in r.stdout and "D=2310 U=16 L=32 R=963" in r.stdout
+
+
+def test_planners_match_oracle_on_random_bounds():
+    """Seeded random B1 / prime ranges: the PRAC plan and PAIR output must equal the oracle's."""
+    import random
+    rng = random.Random(20261018)
+    for _ in range(6):
+        b1 = rng.randrange(7, 60000)
+        ops, adds, dups = E.plan_stage1(b1)
+        ref = O.stage1_trace(b1).decode().replace("S", "")
+        assert "".join(TYPE_CH[b & 7] for b in ops) == ref, b1
+    for _ in range(6):
+        b1 = rng.choice([rng.randrange(40, 5000), rng.randrange(5000, 400000)])
+        lo = b1 + rng.randrange(0, 3) * 1000
+        hi = lo + rng.randrange(1, 2000000)
+        D, U, L, R = E.stage2_params(b1)
+        assert E.pair(lo, hi, D) == O.pair(lo, hi, D), (lo, hi, D)
