@@ -45,6 +45,7 @@ def lib():
     vp = c.c_void_p
     sig = {
         "ecm_b200_create": (c.c_int, [c.POINTER(vp), c.c_int, u32p, c.c_int, c.c_uint32]),
+        "ecm_b200_create_special": (c.c_int, [c.POINTER(vp), c.c_int, u32p, c.c_int, u32p, c.c_int, c.c_uint32]),
         "ecm_b200_destroy": (None, [vp]),
         "ecm_b200_last_error": (c.c_char_p, []),
         "ecm_b200_limbs": (c.c_int, [vp]),
@@ -79,7 +80,7 @@ def lib():
     return L
 
 
-EXPORTS = ["ecm_b200_create", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
+EXPORTS = ["ecm_b200_create", "ecm_b200_create_special", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
            "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
            "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_stage1_progress", "ecm_b200_flush_l2", "ecm_b200_timer", "ecm_b200_read_stage1", "ecm_b200_stage2",
            "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_stage2_program", "ecm_b200_pair", "ecm_b200_stage2_params",
@@ -120,13 +121,23 @@ class EcmContext:
     """One batch of curves sharing N on one GPU (the analogue of the reference's thread_data_t[],
     avx_ecm.h:265-287; one context per GPU replaces one pthread per 8 lanes)."""
 
-    def __init__(self, N, max_curves, device=0):
+    def __init__(self, N, max_curves, device=0, base=None):
+        """base: for a special-form input (see special_form) the number 2^k-1 / 2^k+1 / 2^k-c that N divides;
+        the curve arithmetic is then done modulo base and only the factor checks use N (main.c:597-616)."""
         L = lib()
         self.N = N
-        nlimbs = max(1, (N.bit_length() + 31) // 32)
-        nbuf = (ctypes.c_uint32 * nlimbs)(*[(N >> (32 * k)) & 0xFFFFFFFF for k in range(nlimbs)])
+        self.base = base
+
+        def limbs(v):
+            nl = max(1, (v.bit_length() + 31) // 32)
+            return (ctypes.c_uint32 * nl)(*[(v >> (32 * k)) & 0xFFFFFFFF for k in range(nl)]), nl
+        nbuf, nlimbs = limbs(N)
         self._h = ctypes.c_void_p()
-        _check(L.ecm_b200_create(ctypes.byref(self._h), device, nbuf, nlimbs, max_curves))
+        if base is None:
+            _check(L.ecm_b200_create(ctypes.byref(self._h), device, nbuf, nlimbs, max_curves))
+        else:
+            bbuf, blimbs = limbs(base)
+            _check(L.ecm_b200_create_special(ctypes.byref(self._h), device, bbuf, blimbs, nbuf, nlimbs, max_curves))
         self.nl = L.ecm_b200_limbs(self._h)
         self.max_curves = max_curves
         self.count = 0
@@ -289,13 +300,85 @@ def stage2_params(b1):
     return D.value, U.value, Lw.value, R.value
 
 
-def vececm(N, curves, b1, b2=None, sigma=7, device=0, ctx=None):
+_SMALL_P = [p for p in range(2, 1000) if all(p % q for q in range(2, int(p ** 0.5) + 1))]
+
+
+def primitive_part(k, sign):
+    """The part of 2^k + sign that main.c:187-358 keeps (find_primitive_factor with base 2): with m = k divided
+    by its distinct odd prime factors q_1..q_r, the alternating product over the subsets T of {q_i} of
+    (2^(m*prod T) + sign)^((-1)^(r-|T|)).  Up to three distinct odd primes, like the reference."""
+    odd = []
+    e = k
+    for q in _SMALL_P:
+        while e % q == 0:
+            e //= q
+            if q & 1 and q not in odd:
+                odd.append(q)
+    if len(odd) > 3:
+        raise ValueError("too many distinct odd factors in exponent")
+    m = k
+    for q in odd:
+        m //= q
+    num = den = 1
+    for mask in range(1 << len(odd)):
+        t, bits = 1, 0
+        for i, q in enumerate(odd):
+            if mask >> i & 1:
+                t *= q
+                bits += 1
+        term = (1 << (m * t)) + sign
+        if (len(odd) - bits) % 2 == 0:
+            num *= term
+        else:
+            den *= term
+    return num // den
+
+
+def special_form(N, digitbits=52):
+    """Input classification of main.c:405-521.  Returns dict(kind, k, c, base, n): kind 0 = generic REDC
+    (base None), 1 = 2^k-1, -1 = 2^k+1, c > 1 = pseudo-Mersenne 2^k-c; n = N with the algebraic factors of
+    2^k+-1 removed (main.c:444-457).  A form whose base is so much longer than N that REDC on N is cheaper
+    (word ratio < 0.7, main.c:505-521) is reported as generic, like the reference does."""
+    from math import gcd
+    size_n = N.bit_length()
+    kind, k = 0, size_n
+    for i in range(size_n - 1, 2048):
+        r = pow(2, i, N)
+        if (r - 1) % N == 0:
+            kind, k = 1, i
+            break
+        if (r + 1) % N == 0:
+            kind, k = -1, i
+            break
+        if r.bit_length() < digitbits:
+            if r.bit_length() < 32:           # the reference keeps c in an int (main.c:391,437)
+                kind, k = r, i
+            break
+    n = N
+    if abs(kind) == 1:
+        n = gcd(N, primitive_part(k, -kind))
+    block = 208 if digitbits == 52 else 128
+
+    def maxbits(bits):
+        mb = block
+        while mb <= bits:
+            mb += block
+        return mb
+    if kind and maxbits(n.bit_length()) / maxbits(k) < 0.7:
+        kind = 0
+    if kind == 0:
+        return {"kind": 0, "k": n.bit_length(), "c": 0, "base": None, "n": n}
+    base = (1 << k) - kind if kind > 0 else (1 << k) + 1
+    return {"kind": kind, "k": k, "c": kind, "base": base, "n": n}
+
+
+def vececm(N, curves, b1, b2=None, sigma=7, device=0, ctx=None, base=None):
     """Driver for one batch, mirroring vececm() (ecm.c:1077-1544) with threads=1 semantics:
     curve i runs sigma+i (main.c:757-763).  Returns dict(save_lines, factors=[(sigma, stage, factor)],
-    x, z, acc)."""
+    x, z, acc).  base: see EcmContext (special-form inputs; X, Z, acc are then residues mod base)."""
     own = ctx is None
     if own:
-        ctx = EcmContext(N, curves, device)
+        ctx = EcmContext(N, curves, device, base=base)
     try:
         sig = [sigma + i for i in range(curves)]
         ctx.build_curves(sig)

@@ -17,6 +17,7 @@
 #include <vector>
 #include "../../include/ecm_b200.h"
 #include "calc.hpp"
+#include "special.hpp"
 
 static double now()
 {
@@ -38,10 +39,15 @@ struct Shard {
     std::string error;
 };
 
-static void run_shard(Shard *s, const std::vector<uint32_t> *n32, uint64_t b1, uint64_t b2, bool do2)
+// base32 empty: generic input.  Otherwise the curve arithmetic runs modulo the base number 2^k-c / 2^k+1 and
+// only the factor checks use N (main.c:597-616, ecm.c:1108-1119).
+static void run_shard(Shard *s, const std::vector<uint32_t> *n32, const std::vector<uint32_t> *base32, uint64_t b1, uint64_t b2, bool do2)
 {
     ecm_b200_ctx *ctx = NULL;
-    if (ecm_b200_create(&ctx, s->gpu, n32->data(), (int)n32->size(), s->count)) { s->error = ecm_b200_last_error(); return; }
+    const int rc0 = base32->empty() ? ecm_b200_create(&ctx, s->gpu, n32->data(), (int)n32->size(), s->count)
+                                    : ecm_b200_create_special(&ctx, s->gpu, base32->data(), (int)base32->size(), n32->data(),
+                                                              (int)n32->size(), s->count);
+    if (rc0) { s->error = ecm_b200_last_error(); return; }
     const int L = s->limbs = ecm_b200_limbs(ctx);
     const size_t words = (size_t)L * s->count;
     s->X.resize(words); s->Z.resize(words); s->G1.resize(words); s->f1.resize(s->count);
@@ -89,6 +95,14 @@ int main(int argc, char **argv)
         gmp_printf("%Zd\n", v);
         return 0;
     }
+    if (argc == 3 && strcmp(argv[1], "--classify") == 0) {      // input classification only (main.c:405-521)
+        mpz_t v, b; mpz_init(v); mpz_init(b);
+        std::string e = calc_eval(argv[2], v);
+        if (!e.empty()) { printf("error: %s\n", e.c_str()); return 1; }
+        const SpecialForm f = classify_input(v, b);
+        gmp_printf("kind %ld k %d n %Zd base %Zd\n", f.kind, f.k, v, b);
+        return 0;
+    }
     if (argc < 4) {
         printf("usage: avx-ecm-b200 $input $numcurves $B1 [$gpus] [$B2] [$sigma]\n");
         return 1;
@@ -111,15 +125,23 @@ int main(int argc, char **argv)
     uint64_t sigma0 = (argc >= 7) ? strtoull(argv[6], NULL, 10) : 0;
     if (numcurves < (uint32_t)gpus) numcurves = gpus;
 
+    // Mersenne-like inputs: classification, algebraic-factor removal, special base vs REDC (main.c:405-521)
+    mpz_t base; mpz_init(base);
+    const SpecialForm form = classify_input(N, base);
+    if (mpz_cmp_ui(N, 3) < 0) { printf("nothing left to factor after removing algebraic factors\n"); return 1; }
+
     gmp_printf("commencing parallel ecm on %Zd\n", N);
     const int bits = (int)mpz_sizeinbase(N, 2);
-    printf("ECM has been configured with 32-bit limbs on B200 (%d limbs), GMP_LIMB_BITS = %d\n", (bits + 31) / 32, GMP_LIMB_BITS);
+    const int abits = form.kind ? (int)mpz_sizeinbase(base, 2) : bits;      // width of the arithmetic
+    printf("ECM has been configured with 32-bit limbs on B200 (%d limbs), GMP_LIMB_BITS = %d\n", (abits + 31) / 32, GMP_LIMB_BITS);
     if (sigma0) printf("starting with sigma = %" PRIu64 "\n", sigma0);
     printf("Input has %d bits, using %d GPU(s) (%u curves/GPU)\n", bits, gpus, (numcurves + gpus - 1) / gpus);
 
     std::vector<uint32_t> n32((bits + 31) / 32, 0);
     size_t cnt = 0;
     mpz_export(n32.data(), &cnt, -1, 4, 0, 0, N);
+    std::vector<uint32_t> base32;
+    if (form.kind) { base32.assign((abits + 31) / 32, 0); mpz_export(base32.data(), &cnt, -1, 4, 0, 0, base); }
 
     // contiguous sigma slices, one per GPU; random sigmas when none was given (ecm.c:1564-1570)
     std::vector<Shard> shards(gpus);
@@ -138,7 +160,7 @@ int main(int argc, char **argv)
     }
     printf("\nCommencing curves 0-%u of %u\n", numcurves - 1, numcurves);
     std::vector<std::thread> th;
-    for (int g = 0; g < gpus; g++) th.emplace_back(run_shard, &shards[g], &n32, b1, b2, do2);
+    for (int g = 0; g < gpus; g++) th.emplace_back(run_shard, &shards[g], &n32, &base32, b1, b2, do2);
     for (auto &t : th) t.join();
     double ts1 = 0, ts2 = 0, tb = 0;
     for (auto &s : shards) {

@@ -94,6 +94,8 @@ struct ecm_b200_ctx {
     Engine *eng = nullptr;
     int nl = 0;                 // engine limbs
     Big n;                      // modulus padded to nl limbs
+    Big chk;                    // modulus of the factor checks (= n unless special-form)
+    bool special = false;
     uint32_t max_curves = 0, count = 0, groups = 0;
     uint32_t T = 0, groups_max = 0;   // curves per group (= threads per stage-1 block), groups allocated
     Geom G1{0, 0, NSLOT_S1};
@@ -105,6 +107,7 @@ struct ecm_b200_ctx {
     uint8_t *d_ops = nullptr; size_t d_ops_cap = 0;
     uint32_t *d_io = nullptr; size_t d_io_words = 0;     // staging for host<->device transfers
     void *d_params = nullptr;
+    uint32_t *d_chk = nullptr;  // modulus of the factor checks (the input N), nl limbs
     void *d_flush = nullptr;
     uint8_t *d_flags = nullptr;
     Stage1Plan plan;            // cached for plan.b1
@@ -127,12 +130,37 @@ const char *ecm_b200_last_error(void) { return g_err.c_str(); }
 uint64_t ecm_b200_launch_count(void) { return g_launches.load(); }
 int ecm_b200_limbs(const ecm_b200_ctx *ctx) { return ctx ? ctx->nl : 0; }
 
+static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimbs, const uint32_t *chk, int chklimbs,
+                      uint32_t max_curves);
+
 int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimbs, uint32_t max_curves)
+{
+    return create_ctx(out, device, n, nlimbs, nullptr, 0, max_curves);
+}
+
+int ecm_b200_create_special(ecm_b200_ctx **out, int device, const uint32_t *base, int baselimbs, const uint32_t *n, int nlimbs,
+                            uint32_t max_curves)
+{
+    if (!n || nlimbs < 1) return fail(ECM_B200_EINVAL, "bad argument");
+    return create_ctx(out, device, base, baselimbs, n, nlimbs, max_curves);
+}
+
+// chk != nullptr: special-form input (main.c:405-457, 597-616).  All arithmetic is done modulo the base number
+// `n` = 2^k-1 / 2^k+1 / 2^k-c; the factor checks use the input `chk` (ecm.c:1108-1119); residues are reported
+// mod the base number; a failed inversion leaves the plain gcd / plain operand (no Montgomery form on that path,
+// ecm.c:1903-1946).
+static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimbs, const uint32_t *chk, int chklimbs,
+                      uint32_t max_curves)
 {
     if (!out || !n || nlimbs < 1 || max_curves < 1) return fail(ECM_B200_EINVAL, "bad argument");
     *out = nullptr;
     while (nlimbs > 1 && n[nlimbs - 1] == 0) nlimbs--;
     if (!(n[0] & 1) || (nlimbs == 1 && n[0] < 3)) return fail(ECM_B200_EINVAL, "modulus must be odd and > 1");
+    if (chk) {
+        while (chklimbs > 1 && chk[chklimbs - 1] == 0) chklimbs--;
+        if (!(chk[0] & 1) || (chklimbs == 1 && chk[0] < 3)) return fail(ECM_B200_EINVAL, "input number must be odd and > 1");
+        if (chklimbs > nlimbs) return fail(ECM_B200_EINVAL, "input number is larger than its base number");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
         return fail(ECM_B200_ENODEV, "no usable CUDA device (this engine has no CPU fallback)");
@@ -151,6 +179,13 @@ int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimb
     // reference R: MAXBITS = smallest multiple of 208 strictly above bitlen(N) (main.c:465-483)
     uint32_t maxbits_ref = 208; while (maxbits_ref <= bitlen(c->n)) maxbits_ref += 208;
     Big rri = one; for (uint32_t i = 0; i < maxbits_ref; i++) half_mod(rri, c->n);   // R * 2^-MAXBITS mod N
+    c->chk = c->n;
+    if (chk) {                                            // special form: plain residues, R_ref = 1
+        rri = one;
+        c->chk.assign(nl, 0);
+        for (int i = 0; i < chklimbs; i++) c->chk[i] = chk[i];
+        c->special = true;
+    }
     uint32_t inv = 1; for (int i = 0; i < 5; i++) inv *= 2 - c->n[0] * inv;           // N^-1 mod 2^32
     const uint32_t m0inv = 0u - inv;
     eng->set_params(c->n, one, r2, r3, rri, m0inv);
@@ -195,6 +230,8 @@ int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimb
     c->d_io_words = (size_t)4 * nl * max_curves + 64;
     CUC(cudaMalloc(&c->d_io, c->d_io_words * 4));
     CUC(cudaMalloc(&c->d_flags, (size_t)max_curves * 2 + 64));
+    CUC(cudaMalloc(&c->d_chk, (size_t)nl * 4));
+    CUC(cudaMemcpyAsync(c->d_chk, c->chk.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
     CUC(cudaMalloc(&c->d_params, eng->params_bytes));
     CUC(cudaMemcpyAsync(c->d_params, eng->params_host(), eng->params_bytes, cudaMemcpyHostToDevice, c->stream));
     eng->set_params_device(c->d_params);
@@ -209,7 +246,7 @@ void ecm_b200_destroy(ecm_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_state); cudaFree(c->d_ops); cudaFree(c->d_io); cudaFree(c->d_flags); cudaFree(c->d_params); cudaFree(c->d_flush); cudaFree(c->d_acc); cudaFree(c->d_fail);
+    cudaFree(c->d_state); cudaFree(c->d_ops); cudaFree(c->d_io); cudaFree(c->d_flags); cudaFree(c->d_params); cudaFree(c->d_chk); cudaFree(c->d_flush); cudaFree(c->d_acc); cudaFree(c->d_fail);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -424,7 +461,7 @@ int ecm_b200_read_stage1(ecm_b200_ctx *c, uint32_t *x, uint32_t *z, uint8_t *fac
     uint32_t *dx = c->d_io, *dz = c->d_io + words, *dg = c->d_io + 2 * words;
     const bool want_flag = factor_flag || gcd_out;
     c->eng->read_point(c->stream, c->d_state, c->G1, c->count, 2 * c->p_slot, 2 * c->p_slot + 1, x ? dx : nullptr, dz,
-                       want_flag ? c->d_flags : nullptr, gcd_out ? dg : nullptr);
+                       want_flag ? c->d_flags : nullptr, gcd_out ? dg : nullptr, c->d_chk);
     CU(cudaGetLastError());
     if (x) CU(cudaMemcpyAsync(x, dx, words * 4, cudaMemcpyDeviceToHost, c->stream));
     if (z) CU(cudaMemcpyAsync(z, dz, words * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -590,7 +627,7 @@ int ecm_b200_read_stage2(ecm_b200_ctx *c, uint32_t *acc, uint8_t *factor_flag, u
     const bool want_flag = factor_flag || gcd_out;
     // d_acc is laid out like a one-slot state with cap = count
     c->eng->read_point(c->stream, c->d_acc, Geom{c->count, c->count, 1}, c->count, 0, 0, nullptr, da, want_flag ? c->d_flags : nullptr,
-                       gcd_out ? dg : nullptr);
+                       gcd_out ? dg : nullptr, c->d_chk);
     CU(cudaGetLastError());
     if (acc) CU(cudaMemcpyAsync(acc, da, words * 4, cudaMemcpyDeviceToHost, c->stream));
     if (factor_flag) CU(cudaMemcpyAsync(factor_flag, c->d_flags, c->count, cudaMemcpyDeviceToHost, c->stream));

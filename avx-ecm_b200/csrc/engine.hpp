@@ -23,7 +23,7 @@ struct Engine {
     virtual void load_curves(cudaStream_t st, uint32_t *state, Geom G, uint32_t lanes, uint32_t count, const uint32_t *x, const uint32_t *s) = 0;
     virtual void build_curves(cudaStream_t st, uint32_t *state, Geom G, uint32_t lanes, uint32_t count, const uint32_t *uv, uint8_t *ok) = 0;
     virtual void read_point(cudaStream_t st, const uint32_t *state, Geom G, uint32_t count, uint32_t xs, uint32_t zs,
-                            uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g) = 0;
+                            uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g, const uint32_t *chk) = 0;
     // stage 2
     int threads_s2 = 0, smem_s2 = 0, nslot_s2 = 0;
     virtual void vm2(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, uint32_t *tab, const uint64_t *code,

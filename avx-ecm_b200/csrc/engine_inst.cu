@@ -82,9 +82,9 @@ struct EngineT : Engine {
         count_launch();
     }
     void read_point(cudaStream_t st, const uint32_t *state, Geom G, uint32_t count, uint32_t xs, uint32_t zs,
-                    uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g) override
+                    uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g, const uint32_t *chk) override
     {
-        k_read_point<NL><<<(count + 63) / 64, 64, 0, st>>>(Pg, state, dg(G), count, xs, zs, x, z, flag, g);
+        k_read_point<NL><<<(count + 63) / 64, 64, 0, st>>>(Pg, state, dg(G), count, xs, zs, x, z, flag, g, chk);
         count_launch();
     }
     void fieldop(cudaStream_t st, int op, uint32_t count, const uint32_t *a, const uint32_t *b, uint32_t *r, int repeat) override

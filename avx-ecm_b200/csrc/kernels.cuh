@@ -124,10 +124,21 @@ __device__ __noinline__ bool nm_inverse(uint32_t *inv, uint32_t *g, const uint32
     uint32_t a[NL], i[NL], gg[NL];
 #pragma unroll
     for (int k = 0; k < NL; k++) a[k] = x[k];
-    const bool ok = mod_inverse<NL, true>(i, gg, a, *Pg);
+    const bool ok = mod_inverse<NL, true>(i, gg, a, Pg->n);
 #pragma unroll
     for (int k = 0; k < NL; k++) { inv[k] = i[k]; g[k] = gg[k]; }
     return ok;
+}
+// g = gcd(x, m) for an odd m of NL limbs in global memory (x need not be below m)
+template <int NL>
+__device__ __noinline__ void nm_gcd(uint32_t *g, const uint32_t *x, const uint32_t *m)
+{
+    uint32_t a[NL], i[NL], gg[NL];
+#pragma unroll
+    for (int k = 0; k < NL; k++) a[k] = x[k];
+    mod_inverse<NL, false>(i, gg, a, m);
+#pragma unroll
+    for (int k = 0; k < NL; k++) g[k] = gg[k];
 }
 
 // ---- curve set-up -----------------------------------------------------------------------------
@@ -154,7 +165,12 @@ __global__ void k_load_curves(const ModParams<NL> *Pg, uint32_t *state, Geom G, 
 // [limb][curve]); build_one_curve, ecm.c:1587-1772:
 //   X = u^3 / v^3,  Z = 1,  s = (v-u)^3 (3u+v) / (16 u^3 v)
 // One shared inversion of (v^3 * 16u^3v) replaces the reference's two mpz_invert calls; the
-// quotients are the same residues.  ok[c] = 0 when that product is not invertible mod N.
+// quotients are the same residues.  ok[c] = 0 when that product is not invertible mod N; then the
+// reference's two mpz_invert calls (ecm.c:1745,1759) each leave their output operand untouched
+// when they fail, i.e. s = num * (16 u^3 v invertible ? its inverse : 16 u^3) and
+// X = u^3 * (v^3 invertible ? its inverse : num).  16u^3v is invertible iff the shared product is,
+// so on failure s uses 16u^3 and only v^3 is tried again on its own.  (Common for special-form
+// inputs, where the arithmetic modulus 2^k+-1 keeps its small algebraic factors.)
 template <int NL>
 __global__ void k_build_curves(const ModParams<NL> *Pg, uint32_t *state, Geom G, uint32_t lanes, uint32_t count,
                                const uint32_t *uv, uint8_t *ok)
@@ -179,9 +195,16 @@ __global__ void k_build_curves(const ModParams<NL> *Pg, uint32_t *state, Geom G,
     for (int k = 0; k < 4; k++) nm_addsub<NL>(den, den, den, false, Pg);   // 16 u^3 v
     nm_mul<NL>(t1, den, v3, Pg);                                  // den * v^3   (Montgomery form)
     const bool good = nm_inverse<NL>(inv, g, t1, Pg);             // (den v^3 R)^-1
-    nm_mul<NL>(inv, inv, Pg->r3, Pg);                             // -> (den v^3)^-1 in Montgomery form
-    nm_mul<NL>(t1, inv, den, Pg);                                 // 1/v^3
-    nm_mul<NL>(t2, inv, v3, Pg);                                  // 1/den
+    if (good) {
+        nm_mul<NL>(inv, inv, Pg->r3, Pg);                         // -> (den v^3)^-1 in Montgomery form
+        nm_mul<NL>(t1, inv, den, Pg);                             // 1/v^3
+        nm_mul<NL>(t2, inv, v3, Pg);                              // 1/den
+    } else {
+        for (int k = 0; k < NL; k++) t2[k] = u3[k];
+        for (int k = 0; k < 4; k++) nm_addsub<NL>(t2, t2, t2, false, Pg);      // 16 u^3 stands in for 1/den
+        if (nm_inverse<NL>(inv, g, v3, Pg)) nm_mul<NL>(t1, inv, Pg->r3, Pg);   // 1/v^3 still exists
+        else for (int k = 0; k < NL; k++) t1[k] = num[k];                       // num stands in for 1/v^3
+    }
     nm_mul<NL>(t1, t1, u3, Pg);                                   // X = u^3/v^3
     nm_mul<NL>(t2, t2, num, Pg);                                  // s
     for (int k = 0; k < NL; k++) {
@@ -198,11 +221,11 @@ __global__ void k_build_curves(const ModParams<NL> *Pg, uint32_t *state, Geom G,
 template <int NL>
 __global__ void k_read_point(const ModParams<NL> *Pg, const uint32_t *state, Geom G, uint32_t count,
                              uint32_t xslot, uint32_t zslot, uint32_t *x_out, uint32_t *z_out,
-                             uint8_t *flag, uint32_t *g_out)
+                             uint8_t *flag, uint32_t *g_out, const uint32_t *chk)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= count) return;
-    uint32_t a[NL], one[NL], r[NL], g[NL], dummy[NL];
+    uint32_t a[NL], one[NL], r[NL], g[NL];
     for (int k = 0; k < NL; k++) one[k] = (k == 0);
 #pragma unroll 1
     for (int which = 0; which < 2; which++) {
@@ -215,9 +238,11 @@ __global__ void k_read_point(const ModParams<NL> *Pg, const uint32_t *state, Geo
         }
     }
     if (flag) {                                   // a = Z (Montgomery form; gcd(Z*R,N) = gcd(Z,N))
-        nm_inverse<NL>(dummy, g, a, Pg);
+        // chk = the input N: the arithmetic modulus itself, or for special-form inputs the cofactor
+        // of 2^k+-c that is being factored (ecm.c:1108-1119) -- R stays coprime to it
+        nm_gcd<NL>(g, a, chk);
         bool is_one = (g[0] == 1), is_n = true;
-        for (int k = 0; k < NL; k++) { if (k && g[k]) is_one = false; if (g[k] != Pg->n[k]) is_n = false; }
+        for (int k = 0; k < NL; k++) { if (k && g[k]) is_one = false; if (g[k] != chk[k]) is_n = false; }
         const bool found = !is_one && !is_n;
         flag[c] = found ? 1 : 0;
         if (g_out) for (int k = 0; k < NL; k++) g_out[(size_t)k * count + c] = found ? g[k] : 0;

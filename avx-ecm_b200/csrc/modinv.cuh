@@ -11,13 +11,14 @@ namespace ecmb200 {
 // in : x in [0,N)
 // out: g = gcd(x,N) (g = N for x = 0); if g == 1, inv = x^-1 mod N in [0,N).  Returns g == 1.
 // Invariants: A*x == u, C*x == v (mod N); u,v >= 0; A,C in [0,N).
+// `n` points at the NL limbs of the modulus (any address space); for WANT_INV = false x may exceed N.
 template <int NL, bool WANT_INV>
 __device__ __noinline__ bool mod_inverse(uint32_t (&inv)[NL], uint32_t (&g)[NL], const uint32_t (&x)[NL],
-                                         const ModParams<NL> &P)
+                                         const uint32_t *n)
 {
     uint32_t u[NL], v[NL], A[NL], C[NL];
 #pragma unroll
-    for (int k = 0; k < NL; k++) { u[k] = x[k]; v[k] = P.n[k]; A[k] = (k == 0); C[k] = 0; }
+    for (int k = 0; k < NL; k++) { u[k] = x[k]; v[k] = n[k]; A[k] = (k == 0); C[k] = 0; }
 
     for (;;) {
         uint32_t nz = 0;
@@ -59,18 +60,18 @@ __device__ __noinline__ bool mod_inverse(uint32_t (&inv)[NL], uint32_t (&g)[NL],
             // tn = C - A mod N = -(A-C) mod N : if A-C borrowed (A<C): C-A = -(t) plain; else N - t (or 0)
             // compute both variants cheaply: m1 = t + (N & bo)  == (A - C) mod N
             uint32_t m1[NL];
-            m1[0] = add3_cc(t[0], P.n[0] & bo);
+            m1[0] = add3_cc(t[0], n[0] & bo);
 #pragma unroll
-            for (int k = 1; k < NL; k++) m1[k] = (k == NL - 1) ? addc3(t[k], P.n[k] & bo) : addc3_cc(t[k], P.n[k] & bo);
+            for (int k = 1; k < NL; k++) m1[k] = (k == NL - 1) ? addc3(t[k], n[k] & bo) : addc3_cc(t[k], n[k] & bo);
             // m2 = (C - A) mod N = (N - m1) if m1 != 0 else 0
             uint32_t m1nz = 0;
 #pragma unroll
             for (int k = 0; k < NL; k++) m1nz |= m1[k];
             const uint32_t nzmask = m1nz ? 0xffffffffu : 0u;
             uint32_t m2[NL];
-            m2[0] = sub3_cc(P.n[0] & nzmask, m1[0]);
+            m2[0] = sub3_cc(n[0] & nzmask, m1[0]);
 #pragma unroll
-            for (int k = 1; k < NL; k++) m2[k] = (k == NL - 1) ? subc3(P.n[k] & nzmask, m1[k]) : subc3_cc(P.n[k] & nzmask, m1[k]);
+            for (int k = 1; k < NL; k++) m2[k] = (k == NL - 1) ? subc3(n[k] & nzmask, m1[k]) : subc3_cc(n[k] & nzmask, m1[k]);
 #pragma unroll
             for (int k = 0; k < NL; k++) {
                 const uint32_t ao = A[k];
@@ -79,9 +80,9 @@ __device__ __noinline__ bool mod_inverse(uint32_t (&inv)[NL], uint32_t (&g)[NL],
             }
             // A = A/2 mod N : if A odd add N first (may carry out of NL limbs)
             const uint32_t ao = 0u - (A[0] & 1u);
-            A[0] = add3_cc(A[0], P.n[0] & ao);
+            A[0] = add3_cc(A[0], n[0] & ao);
 #pragma unroll
-            for (int k = 1; k < NL; k++) A[k] = addc3_cc(A[k], P.n[k] & ao);
+            for (int k = 1; k < NL; k++) A[k] = addc3_cc(A[k], n[k] & ao);
             const uint32_t top = addc3(0, 0);
 #pragma unroll
             for (int k = 0; k < NL; k++) A[k] = (k == NL - 1) ? __funnelshift_r(A[k], top, 1) : __funnelshift_r(A[k], A[k + 1], 1);

@@ -39,6 +39,14 @@ typedef struct ecm_b200_ctx ecm_b200_ctx;
  * the batch.  The Montgomery constants (R = 2^(32*k), one = R mod N, -N^-1 mod 2^32) are derived
  * here; residues never depend on R.                                         */
 int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimbs, uint32_t max_curves);
+/* Special-form inputs (replaces the isMersenne set-up, main.c:405-457 and 597-616): n divides
+ * base = 2^k-1, 2^k+1 or 2^k-c.  Like the reference, all curve arithmetic is then done modulo
+ * `base` (ecm_b200_limbs() >= baselimbs), residues are reported modulo `base` (ecm.c:1327-1380
+ * prints them that way), the factor checks of read_stage1/read_stage2 use gcd(., n)
+ * (ecm.c:1108-1119) and a failed stage-2 inversion leaves plain values (ecm.c:1903-1946).
+ * Detecting the form and removing algebraic factors is the caller's job (main.c:405-457).    */
+int ecm_b200_create_special(ecm_b200_ctx **out, int device, const uint32_t *base, int baselimbs,
+                            const uint32_t *n, int nlimbs, uint32_t max_curves);
 void ecm_b200_destroy(ecm_b200_ctx *ctx);
 const char *ecm_b200_last_error(void);
 /* number of 32-bit limbs the engine computes with (>= nlimbs of N; kernels exist for a fixed set) */

@@ -49,6 +49,7 @@ typedef struct {
     uint32_t npb;
     int found_inv;                    /* any inversion failure seen           */
     mpz_t rref_inv;                   /* 2^-MAXBITS mod N, MAXBITS of the 52-bit build (main.c:465-483) */
+    mpz_t nchk;                       /* modulus of the factor checks: n, or the input cofactor (nhat) in Mersenne mode */
 } owork;
 
 static void fmul(owork *w, mpz_t c, const mpz_t a, const mpz_t b)   /* vecmulmod_ptr */
@@ -600,7 +601,13 @@ static void ecm_stage2_pair(owork *w, opt *P, uint32_t steps, const uint32_t *pm
 /* ------------------------------------------------------------------ */
 /* work alloc                                                          */
 /* ------------------------------------------------------------------ */
-static owork *work_new(const char *n_hex)
+/* m_hex == NULL: generic Montgomery path, arithmetic and checks mod N.
+ * m_hex != NULL: special-form path (main.c:405-457, 597-616): all arithmetic mod the base number
+ * M = 2^k-1 / 2^k+1 / 2^k-c given in m_hex, residues are plain (no Montgomery form, one = 1), the
+ * reference's lazily reduced representatives lie in [0,2^k) and equal the canonical residue mod M
+ * except on the zero class (probability ~c/2^k per operation; vecarith52.c:880-1025, 4613-4801);
+ * gcd checks use the original input N (ecm.c:1108-1119).                                        */
+static owork *work_new2(const char *n_hex, const char *m_hex)
 {
     owork *w = (owork *)calloc(1, sizeof(owork));
     mpz_init(w->n); mpz_init(w->s);
@@ -608,9 +615,14 @@ static owork *work_new(const char *n_hex)
     mpz_init(w->tt1); mpz_init(w->tt2); mpz_init(w->tt3); mpz_init(w->tt4);
     pt_init(&w->pt1); pt_init(&w->pt2); pt_init(&w->pt3); pt_init(&w->pt4);
     pt_init(&w->Pad); pt_init(&w->Pd); mpz_init(w->acc);
-    if (mpz_set_str(w->n, n_hex, 16) != 0) { free(w); return NULL; }
-    {   /* main.c:465-483: MAXBITS = smallest multiple of 208 strictly above bitlen(N) */
+    mpz_init(w->nchk);
+    if (mpz_set_str(w->nchk, n_hex, 16) != 0) { free(w); return NULL; }
+    if (m_hex) {
+        if (mpz_set_str(w->n, m_hex, 16) != 0) { free(w); return NULL; }
+        mpz_init(w->rref_inv); mpz_set_ui(w->rref_inv, 1);      /* failure lanes keep plain g and a (ecm.c:1903-1946) */
+    } else {   /* main.c:465-483: MAXBITS = smallest multiple of 208 strictly above bitlen(N) */
         unsigned long maxbits = 208;
+        mpz_set(w->n, w->nchk);
         mpz_init(w->rref_inv);
         while (maxbits <= mpz_sizeinbase(w->n, 2)) maxbits += 208;
         mpz_set_ui(w->rref_inv, 1); mpz_mul_2exp(w->rref_inv, w->rref_inv, maxbits);
@@ -618,6 +630,7 @@ static owork *work_new(const char *n_hex)
     }
     return w;
 }
+static owork *work_new(const char *n_hex) { return work_new2(n_hex, NULL); }
 static void work_free(owork *w)
 {
     uint32_t i;
@@ -628,7 +641,7 @@ static void work_free(owork *w)
     mpz_clear(w->sum1); mpz_clear(w->diff1); mpz_clear(w->sum2); mpz_clear(w->diff2);
     mpz_clear(w->tt1); mpz_clear(w->tt2); mpz_clear(w->tt3); mpz_clear(w->tt4);
     pt_clear(&w->pt1); pt_clear(&w->pt2); pt_clear(&w->pt3); pt_clear(&w->pt4);
-    pt_clear(&w->Pad); pt_clear(&w->Pd); mpz_clear(w->acc); mpz_clear(w->rref_inv);
+    pt_clear(&w->Pad); pt_clear(&w->Pd); mpz_clear(w->acc); mpz_clear(w->rref_inv); mpz_clear(w->nchk);
     free(w);
 }
 
@@ -667,10 +680,10 @@ int oracle_build_curve(const char *n_hex, uint64_t sigma, char *x_hex, char *s_h
  *  f2_dec      : stage-2 factor ("0" if none)    (ecm.c:1485-1497)
  *  counters[8] : s1 ptadds, s1 ptdups, s2 ptadds, s2 numinv, s2 paired, pairmap steps, found_inv, last amin
  * do_stage2 follows main.c:543-552 (b2 <= b1 disables stage 2).               */
-int oracle_ecm_curve(const char *n_hex, uint64_t b1, uint64_t b2, uint64_t sigma,
+static int ecm_curve(const char *n_hex, const char *m_hex, uint64_t b1, uint64_t b2, uint64_t sigma,
     char *x_hex, char *z_hex, char *f1_dec, char *acc_hex, char *f2_dec, uint32_t *counters)
 {
-    owork *w = work_new(n_hex);
+    owork *w = work_new2(n_hex, m_hex);
     opt P; mpz_t A, f;
     uint64_t nump, *primes, p;
     int do2 = b2 > b1;
@@ -685,7 +698,7 @@ int oracle_ecm_curve(const char *n_hex, uint64_t b1, uint64_t b2, uint64_t sigma
     free(primes);
     counters[0] = w->ptadds; counters[1] = w->ptdups;
     mpz_get_str(x_hex, 16, P.X); mpz_get_str(z_hex, 16, P.Z);
-    if (!check_factor(P.Z, w->n, f)) mpz_set_ui(f, 0);
+    if (!check_factor(P.Z, w->nchk, f)) mpz_set_ui(f, 0);
     mpz_get_str(f1_dec, 10, f);
     acc_hex[0] = 0; strcpy(f2_dec, "0");
 
@@ -708,12 +721,25 @@ int oracle_ecm_curve(const char *n_hex, uint64_t b1, uint64_t b2, uint64_t sigma
         counters[2] = w->ptadds; counters[3] = w->numinv; counters[4] = w->paired;
         counters[6] = w->found_inv; counters[7] = w->amin;
         mpz_get_str(acc_hex, 16, w->acc);
-        if (!check_factor(w->acc, w->n, f)) mpz_set_ui(f, 0);
+        if (!check_factor(w->acc, w->nchk, f)) mpz_set_ui(f, 0);
         mpz_get_str(f2_dec, 10, f);
     }
     pt_clear(&P); mpz_clear(A); mpz_clear(f); work_free(w);
     return 0;
 }
+
+int oracle_ecm_curve(const char *n_hex, uint64_t b1, uint64_t b2, uint64_t sigma,
+    char *x_hex, char *z_hex, char *f1_dec, char *acc_hex, char *f2_dec, uint32_t *counters)
+{ return ecm_curve(n_hex, NULL, b1, b2, sigma, x_hex, z_hex, f1_dec, acc_hex, f2_dec, counters); }
+
+/* Special-form inputs: n_hex = the input cofactor after algebraic-factor removal (what the save file
+ * prints as N), m_hex = the base number all arithmetic is done against.  Buffers must hold hexlen(M)+2. */
+int oracle_ecm_curve_special(const char *n_hex, const char *m_hex, uint64_t b1, uint64_t b2, uint64_t sigma,
+    char *x_hex, char *z_hex, char *f1_dec, char *acc_hex, char *f2_dec, uint32_t *counters)
+{ return ecm_curve(n_hex, m_hex, b1, b2, sigma, x_hex, z_hex, f1_dec, acc_hex, f2_dec, counters); }
+
+int oracle_build_curve_special(const char *m_hex, uint64_t sigma, char *x_hex, char *s_hex)
+{ return oracle_build_curve(m_hex, sigma, x_hex, s_hex); }
 
 /* The exact save_b1.txt line (ecm.c:1372-1380). */
 int oracle_save_line(const char *n_hex, uint64_t b1, uint64_t sigma, const char *x_hex,

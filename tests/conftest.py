@@ -34,3 +34,8 @@ def golden_factor(g, sigma, stage):
         if int(f["sigma"]) == sigma and f["stage"] == stage:
             return int(f["factor"])
     return 0
+
+
+def golden_base(g):
+    """Base number 2^k-1 / 2^k+1 / 2^k-c of a special-form golden case (None for generic inputs)."""
+    return int(g["base"]) if g.get("base") else None

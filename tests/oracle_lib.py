@@ -22,6 +22,8 @@ def lib():
         u64, u32, cp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_char_p
         L.oracle_ecm_curve.argtypes = [cp, u64, u64, u64, cp, cp, cp, cp, cp, ctypes.POINTER(u32)]
         L.oracle_ecm_curve.restype = ctypes.c_int
+        L.oracle_ecm_curve_special.argtypes = [cp, cp, u64, u64, u64, cp, cp, cp, cp, cp, ctypes.POINTER(u32)]
+        L.oracle_ecm_curve_special.restype = ctypes.c_int
         L.oracle_build_curve.argtypes = [cp, u64, cp, cp]
         L.oracle_save_line.argtypes = [cp, u64, u64, cp, cp, cp, ctypes.c_size_t]
         L.oracle_pair.argtypes = [u64, u64, u32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), u32,
@@ -39,15 +41,19 @@ def lib():
     return _lib
 
 
-def ecm_curve(N, b1, b2, sigma):
-    """Run one curve. Returns dict(x, z, f1, acc, f2, counters, save_line)."""
+def ecm_curve(N, b1, b2, sigma, M=None):
+    """Run one curve. Returns dict(x, z, f1, acc, f2, counters, save_line).
+    M: base number of a special-form input (arithmetic mod M, checks and save line with N)."""
     L = lib()
     nh = ("%x" % N).encode()
-    cap = len(nh) + 16
+    cap = len(nh if M is None else "%x" % M) + 16
     x, z, acc = (ctypes.create_string_buffer(cap) for _ in range(3))
     f1, f2 = (ctypes.create_string_buffer(2 * cap) for _ in range(2))
     cnt = (ctypes.c_uint32 * 8)()
-    rc = L.oracle_ecm_curve(nh, b1, b2, sigma, x, z, f1, acc, f2, cnt)
+    if M is None:
+        rc = L.oracle_ecm_curve(nh, b1, b2, sigma, x, z, f1, acc, f2, cnt)
+    else:
+        rc = L.oracle_ecm_curve_special(nh, ("%x" % M).encode(), b1, b2, sigma, x, z, f1, acc, f2, cnt)
     assert rc == 0
     line = ctypes.create_string_buffer(4 * cap + 256)
     L.oracle_save_line(nh, b1, sigma, x.value, z.value, line, len(line))

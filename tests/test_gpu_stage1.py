@@ -1,7 +1,7 @@
 """GPU parity of curve construction + stage 1 against the golden vectors of the compiled
 reference (byte-identical save_b1.txt lines) and against the oracle, through the C ABI."""
 import pytest
-from conftest import GOLDEN, golden_factor, composites
+from conftest import GOLDEN, golden_factor, golden_base, composites
 import oracle_lib as O
 import avx_ecm_b200 as E
 
@@ -19,11 +19,44 @@ def test_stage1_matches_reference_golden(name):
     g = GOLDEN[name]
     N, b1 = int(g["n"]), g["b1"]
     lanes = len(g["save_lines"])
-    r = E.vececm(N, lanes, b1, b2=b1, sigma=int(g["sigma0"]))
+    r = E.vececm(N, lanes, b1, b2=b1, sigma=int(g["sigma0"]), base=golden_base(g))
     assert r["save_lines"] == g["save_lines"]
     assert r["z"] == [int(z, 16) for z in g["z1_true_hex"]]
     exp = [(int(g["sigma0"]) + i, 1, golden_factor(g, int(g["sigma0"]) + i, 1)) for i in range(lanes)]
     assert r["factors"] == [e for e in exp if e[2]]
+
+
+def test_curve_construction_with_failed_inversions_matches_oracle():
+    """Special-form inputs keep the small algebraic factors of 2^k+-1 in the arithmetic modulus, so the two
+    mpz_invert calls of build_one_curve (ecm.c:1745,1759) fail routinely and leave their outputs untouched.
+    11 | base: sigma = 15 makes u = sigma^2-5 non-invertible (v still is), sigma = 22 makes v non-invertible."""
+    base = 11 * ((1 << 200) + 235)
+    sig = [7, 15, 22, 26, 33, 1000003, 2 ** 63 + 11, 37]
+    ctx = E.EcmContext(base, len(sig), base=base)
+    try:
+        ctx.build_curves(sig)
+        x, z, _ = ctx.read_stage1()
+        ctx.stage1(500)
+        x1, z1, f1 = ctx.read_stage1()
+    finally:
+        ctx.close()
+    for i, s in enumerate(sig):
+        ox, _ = O.build_curve(base, s)
+        assert (x[i], z[i]) == (ox, 1), "sigma %d" % s
+        o = O.ecm_curve(base, 500, 500, s, M=base)
+        assert (x1[i], z1[i], f1[i]) == (o["x"], o["z"], o["f1"]), "sigma %d" % s
+
+
+def test_special_base_2k_plus_1_divisible_by_3():
+    # (2^523+1)/3: every third sigma has a non-invertible v^3 (3 | 4 sigma); residues are reported mod 2^523+1
+    base = 2 ** 523 + 1
+    N = base // 3
+    sig = [1000003 + i for i in range(12)]
+    r = E.vececm(N, len(sig), 300, b2=300, sigma=sig[0], base=base)
+    for i, s in enumerate(sig):
+        o = O.ecm_curve(N, 300, 300, s, M=base)
+        assert r["save_lines"][i] == o["save_line"]
+        assert r["z"][i] == o["z"]
 
 
 def test_curve_construction_matches_oracle():

@@ -2,7 +2,7 @@
 vectors of the compiled reference: the stage-2 accumulator of every curve (true residue), the
 factors reported in stage 1 and stage 2, and the op counters.  Through the C ABI."""
 import pytest
-from conftest import GOLDEN, golden_factor, composites
+from conftest import GOLDEN, golden_factor, golden_base, composites
 import oracle_lib as O
 import avx_ecm_b200 as E
 
@@ -18,7 +18,7 @@ def test_stage2_matches_reference_golden(name):
     g = GOLDEN[name]
     N, b1, b2, s0 = int(g["n"]), g["b1"], g["b2"], int(g["sigma0"])
     lanes = len(g["save_lines"])
-    ctx = E.EcmContext(N, lanes)
+    ctx = E.EcmContext(N, lanes, base=golden_base(g))
     try:
         r = E.vececm(N, lanes, b1, b2, sigma=s0, ctx=ctx)
         cnt = ctx.stage2_counters()
@@ -74,11 +74,11 @@ def test_cli_writes_reference_files(tmp_path):
     import os, re, subprocess
     from conftest import ROOT
     cli = os.path.join(ROOT, "avx-ecm_b200", "avx-ecm-b200")
-    for name in ("readme508_b1_5e4", "small96_D210"):
+    for name in ("readme508_b1_5e4", "small96_D210", "special_m277", "special_p523", "special_pm220_57", "special_redc"):
         g = GOLDEN[name]
         d = tmp_path / name
         d.mkdir()
-        expr = "fib(791)/13/677/216416017" if name.startswith("readme") else g["n"]
+        expr = "fib(791)/13/677/216416017" if name.startswith("readme") else g.get("expr", g["n"])
         out = subprocess.run([cli, expr, str(len(g["save_lines"])), str(g["b1"]), "1", str(g["b2"]), g["sigma0"]],
                              cwd=d, capture_output=True, text=True, check=True).stdout
         assert open(d / "save_b1.txt").read() == "".join(g["save_lines"])

@@ -3,7 +3,7 @@ unmodified reference (tools/gen_golden.py -> tests/golden/*.json): save_b1.txt l
 for byte, stage-1 Z, stage-2 accumulator, reported factors and the reference's op counters.
 """
 import pytest
-from conftest import GOLDEN, golden_factor
+from conftest import GOLDEN, golden_factor, golden_base
 import oracle_lib as O
 
 
@@ -26,7 +26,7 @@ def test_oracle_matches_reference(name):
     c = g["counts"]
     for i in lanes_for(g):
         sigma = int(g["sigma0"]) + i
-        r = O.ecm_curve(N, b1, b2, sigma)
+        r = O.ecm_curve(N, b1, b2, sigma, M=golden_base(g))
         assert r["save_line"] == g["save_lines"][i]
         assert r["z"] == int(g["z1_true_hex"][i], 16)
         assert r["f1"] == golden_factor(g, sigma, 1)

@@ -159,8 +159,77 @@ def run_case(name, N, curves, B1, B2, sigma0):
     }
 
 
+def special_cases():
+    """Special-form inputs (main.c:405-457): given to the reference as expressions, like a user would.
+    sigma0 is 'random-looking' on purpose: with tiny sigmas the first residues mod 2^k+-1 contain words that are
+    exactly 0 or 2^52-1, which trips the reference's carry helpers (vecarith52.c:102-116 report a carry-out
+    whenever the word is all-ones / zero, even without a carry-in) in a lane-coupled way no per-curve engine can
+    reproduce -- see DESIGN.md."""
+    return [
+        # name, expression, curves, B1, B2, sigma0
+        ("special_m277", "2^277-1", 8, 2000, 200000, 1000003),
+        ("special_p523", "(2^523+1)/3", 8, 2000, 200000, 1000003),          # base divisible by 3: inversions fail
+        ("special_pm220_69", "2^220-69", 8, 2000, 200000, 1000003),
+        ("special_pm220_57", "2^220-57", 8, 3000, 300000, 424242421),
+        ("special_m127x", "(2^254-1)/(2^127-1)/3", 8, 1000, 100000, 77777771),   # 2^127+1 over 3: found as 2^127+1
+        ("special_redc", "36667531*129175771*58052548129*83207209", 8, 2000, 200000, 1000003),  # | 2^523+1, REDC wins
+    ]
+
+
+def run_special_case(name, expr, curves, B1, B2, sigma0):
+    with tempfile.TemporaryDirectory() as d:
+        tap = os.path.join(d, "tap.log")
+        env = dict(os.environ, GCD_TAP_FILE=tap, LD_PRELOAD=TAP)
+        out = subprocess.run([REF, expr, str(curves), str(B1), "1", str(B2), str(sigma0)],
+                             cwd=d, env=env, capture_output=True, text=True, check=True).stdout
+        save = open(os.path.join(d, "save_b1.txt")).read().splitlines(keepends=True)
+        taps = [l.split()[1:] for l in open(tap).read().splitlines()]
+    N = int(re.search(r"commencing parallel ecm on (\d+)", out).group(1))
+    m = re.search(r"Using special (?:pseudo-)?Mersenne mod for factor of: 2\^(\d+)([-+])(\d+)", out)
+    kind, k, base = 0, N.bit_length(), None
+    if m:
+        k, c = int(m.group(1)), int(m.group(3))
+        kind = c if m.group(2) == "-" else -1
+        base = (1 << k) - c if kind > 0 else (1 << k) + 1
+    maxbits = int(re.search(r"Choosing MAXBITS = (\d+)", out).group(1))
+    Rinv = 1 if base else pow(1 << maxbits, -1, N)
+    mod = base or N
+    if abs(kind) == 1:
+        taps = taps[1:]                     # main.c:456 gcd(input, primitive part)
+    calls = [(int(a, 16), int(b, 16)) for a, b in taps if len(b) and int(b, 16) == N]
+    fails = [(int(a, 16), int(b, 16)) for a, b in taps if base and int(b, 16) == base]
+    z1 = [a * Rinv % mod for a, _ in calls[:8]]
+    acc = [a * Rinv % mod for a, _ in calls[-8:]] if B2 > B1 else []
+    factors = []
+    for mm in re.finditer(r"found \S+ factor (\d+) in stage (\d) \(B\d = \d+\): thread 0, vec (\d+), sigma (\d+)", out):
+        factors.append({"factor": mm.group(1), "stage": int(mm.group(2)), "lane": int(mm.group(3)), "sigma": mm.group(4)})
+    cnt = {}
+    mm = re.search(r"with (\d+) point-adds and (\d+) point-doubles", out)
+    cnt["s1_ptadds"], cnt["s1_ptdups"] = int(mm.group(1)), int(mm.group(2))
+    if B2 > B1:
+        mm = re.search(r"performed (\d+) pt-adds, (\d+) inversions, and (\d+) pair-muls", out)
+        cnt["s2_ptadds"], cnt["s2_numinv"], cnt["s2_paired"] = map(int, mm.groups())
+        cnt["pairmap_steps"] = sum(int(x) for x in re.findall(r"pairmap step 0 of (\d+)", out))
+    return {
+        "name": name, "expr": expr, "n": str(N), "kind": kind, "k": k, "base": str(base) if base else None,
+        "curves_requested": curves, "b1": B1, "b2": B2, "sigma0": str(sigma0), "maxbits_ref": maxbits,
+        "redc_forced": "determined to be faster by REDC" in out,
+        "save_lines": save[:8], "z1_true_hex": [hex(x)[2:] for x in z1], "acc_true_hex": [hex(x)[2:] for x in acc],
+        "inv_fail_gcd_calls": len(fails), "factors": factors, "counts": cnt,
+    }
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:2] == ["special"]:
+        for c in special_cases():
+            if sys.argv[2:] and c[0] not in sys.argv[2:]:
+                continue
+            g = run_special_case(*c)
+            json.dump(g, open(os.path.join(OUT, c[0] + ".json"), "w"), indent=1)
+            print(c[0], "kind", g["kind"], "k", g["k"], "redc", g["redc_forced"], "factors",
+                  [(f["sigma"], f["stage"], f["factor"]) for f in g["factors"]], g["counts"], "invfail", g["inv_fail_gcd_calls"], flush=True)
+        return
     comp = {k: str(v) for k, v in composites().items()}
     json.dump(comp, open(os.path.join(OUT, "composites.json"), "w"), indent=1)
     want = set(sys.argv[1:])
