@@ -31,8 +31,18 @@ build() { # name extra-flags
   gcc $CFLAGS $2 $FILES "$HERE/shim/ref_stub.c" -o "$OUT/$1" "$GMPLIB" -lm -lpthread
   echo "built $OUT/$1"
 }
+# fieldop-ref: the reference's special-form field operators behind a one-op-per-line driver
+# (shim/fieldop_harness.c); the reference's main() is renamed on the command line, not in its source
+build_harness() {
+  if [ -x "$OUT/fieldop-ref" ] && [ "$OUT/fieldop-ref" -nt "$REF/vecarith52.c" ] && [ "$OUT/fieldop-ref" -nt "$HERE/shim/fieldop_harness.c" ]; then return; fi
+  T="$(mktemp -d)"
+  ( cd "$T" && gcc $CFLAGS -Dmain=ref_main -c $FILES "$HERE/shim/ref_stub.c" && gcc $CFLAGS -c "$HERE/shim/fieldop_harness.c" -o harness_main.o \
+    && gcc *.o -o "$OUT/fieldop-ref" "$GMPLIB" -lm -lpthread ) && echo "built $OUT/fieldop-ref"
+  rm -rf "$T"
+}
 build avx-ecm-ref "" &
 build avx-ecm-ref32 "-DDIGITBITS=32" &
+build_harness &
 wait
 if [ ! -f "$OUT/gcd_tap.so" ] || [ "$HERE/shim/gcd_tap.c" -nt "$OUT/gcd_tap.so" ]; then
   gcc -O2 -fPIC -shared -I"$HERE/shim" "$HERE/shim/gcd_tap.c" -o "$OUT/gcd_tap.so" -ldl "$GMPLIB"

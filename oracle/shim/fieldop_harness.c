@@ -6,7 +6,10 @@
  * they lie (main.c is compiled with -Dmain=ref_main; nothing is copied).
  *
  * usage: fieldop-ref nbits c      (c = 1: 2^nbits-1, c = -1: 2^nbits+1, c > 1: 2^nbits-c)
- * stdin lines:  mul A B | sqr A | add A B | sub A B | addsub A B     (hex operands, lane 0)
+ * stdin lines:  mul A B | sqr A | add A B | sub A B | addsub A B     (hex operands, broadcast to all lanes)
+ *               mul8 A0 B0 .. A7 B7      eight independent lanes, eight results
+ *               dup X0 Z0 S0 .. X7 Z7 S7 the doubling of ecm_stage1 (ecm.c:1819-1821 + vec_duplicate) on eight
+ *                                        lanes with the reference's buffer reuse; prints lane 0's X Z
  * stdout: result(s) in hex, one line per op.                                              */
 #include "avx_ecm.h"
 
@@ -56,11 +59,7 @@ int main(int argc, char **argv)
             vecmulmod52_mersenne(tt1, tt2, PX, md->n, tt4, md);
             vecsubmod52_mersenne(tt2, tt1, tt3, md);
             vecmulmod52_mersenne(tt3, ws, tt2, md->n, tt4, md);
-            extract_bignum_from_vec_to_mpz(t, tt2, 0, NWORDS); gmp_printf("tt2pre=%Zx\n", t);
             vecaddmod52_mersenne(tt2, tt1, tt2, md);
-            extract_bignum_from_vec_to_mpz(t, tt1, 0, NWORDS); gmp_printf("tt1=%Zx\n", t);
-            extract_bignum_from_vec_to_mpz(t, tt3, 0, NWORDS); gmp_printf("tt3=%Zx\n", t);
-            extract_bignum_from_vec_to_mpz(t, tt2, 0, NWORDS); gmp_printf("tt2=%Zx\n", t);
             vecmulmod52_mersenne(tt2, tt3, PZ, md->n, tt4, md);
             extract_bignum_from_vec_to_mpz(t, PX, 0, NWORDS); gmp_printf("%Zx", t);
             extract_bignum_from_vec_to_mpz(t, PZ, 0, NWORDS); gmp_printf(" %Zx\n", t);
