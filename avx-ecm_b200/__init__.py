@@ -46,6 +46,7 @@ def lib():
     sig = {
         "ecm_b200_create": (c.c_int, [c.POINTER(vp), c.c_int, u32p, c.c_int, c.c_uint32]),
         "ecm_b200_create_special": (c.c_int, [c.POINTER(vp), c.c_int, u32p, c.c_int, u32p, c.c_int, c.c_uint32]),
+        "ecm_b200_uses_fold": (c.c_int, [vp]),
         "ecm_b200_destroy": (None, [vp]),
         "ecm_b200_last_error": (c.c_char_p, []),
         "ecm_b200_limbs": (c.c_int, [vp]),
@@ -80,7 +81,7 @@ def lib():
     return L
 
 
-EXPORTS = ["ecm_b200_create", "ecm_b200_create_special", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
+EXPORTS = ["ecm_b200_create", "ecm_b200_create_special", "ecm_b200_uses_fold", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
            "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
            "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_stage1_progress", "ecm_b200_flush_l2", "ecm_b200_timer", "ecm_b200_read_stage1", "ecm_b200_stage2",
            "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_stage2_program", "ecm_b200_pair", "ecm_b200_stage2_params",
@@ -139,6 +140,7 @@ class EcmContext:
             bbuf, blimbs = limbs(base)
             _check(L.ecm_b200_create_special(ctypes.byref(self._h), device, bbuf, blimbs, nbuf, nlimbs, max_curves))
         self.nl = L.ecm_b200_limbs(self._h)
+        self.uses_fold = bool(L.ecm_b200_uses_fold(self._h))     # shift-and-fold kernels instead of Montgomery
         self.max_curves = max_curves
         self.count = 0
         self.sigmas = []

@@ -76,6 +76,11 @@ namespace ecmb200 {
 #define X(n) Engine *make_engine_##n();
 ECM_B200_LIMB_SET
 #undef X
+#ifdef ECM_B200_SPECIAL_LIMB_SET
+#define X(n) Engine *make_engine_sp_##n();
+ECM_B200_SPECIAL_LIMB_SET
+#undef X
+#endif
 void count_launch() { g_launches++; }
 }
 namespace {
@@ -85,6 +90,35 @@ Engine *make_engine(int nlimbs)
     ECM_B200_LIMB_SET
 #undef X
     return nullptr;
+}
+// shift-and-fold kernels for a base 2^kbits -+ c, when they were compiled for a suitable limb count
+Engine *make_special_engine(int nlimbs, uint32_t kbits)
+{
+    (void)nlimbs; (void)kbits;
+#ifdef ECM_B200_SPECIAL_LIMB_SET
+    // the smallest compiled limb count that holds the base AND has bit kbits strictly inside its limbs
+#define X(n) if (nlimbs <= n) { Engine *e = make_engine_sp_##n(); if (e->serves_special(kbits)) return e; delete e; }
+    ECM_B200_SPECIAL_LIMB_SET
+#undef X
+#endif
+    return nullptr;
+}
+// n = 2^k - c with 1 <= c < 2^31, or n = 2^k + 1 ?  (the forms main.c:408-441 detects)
+bool special_shape(const uint32_t *n, int nlimbs, int *kind, uint32_t *kbits, uint32_t *cval)
+{
+    Big v(n, n + nlimbs);
+    const uint32_t bl = bitlen(v);
+    if (bl < 64) return false;
+    // 2^k + 1: bit k, bit 0, nothing between
+    bool plus = (v[0] == 1) && (v[(bl - 1) >> 5] == (1u << ((bl - 1) & 31)));
+    for (int i = 1; plus && i < (int)((bl - 1) >> 5); i++) if (v[i]) plus = false;
+    if (plus && bl >= 65) { *kind = -1; *kbits = bl - 1; *cval = 1; return true; }
+    // 2^k - c, k = bitlen: every bit of limbs 1.. below k set, limb 0 = 2^32 - c
+    for (uint32_t b = 32; b < bl; b++) if (!((v[b >> 5] >> (b & 31)) & 1u)) return false;
+    const uint32_t c = 0u - v[0];
+    if (c == 0 || c >= (1u << 31)) return false;
+    *kind = 1; *kbits = bl; *cval = c;
+    return true;
 }
 
 }  // namespace
@@ -96,6 +130,7 @@ struct ecm_b200_ctx {
     Big n;                      // modulus padded to nl limbs
     Big chk;                    // modulus of the factor checks (= n unless special-form)
     bool special = false;
+    bool fold = false;          // shift-and-fold kernels (special-form base) instead of Montgomery
     uint32_t max_curves = 0, count = 0, groups = 0;
     uint32_t T = 0, groups_max = 0;   // curves per group (= threads per stage-1 block), groups allocated
     Geom G1{0, 0, NSLOT_S1};
@@ -129,6 +164,7 @@ extern "C" {
 const char *ecm_b200_last_error(void) { return g_err.c_str(); }
 uint64_t ecm_b200_launch_count(void) { return g_launches.load(); }
 int ecm_b200_limbs(const ecm_b200_ctx *ctx) { return ctx ? ctx->nl : 0; }
+int ecm_b200_uses_fold(const ecm_b200_ctx *ctx) { return ctx && ctx->fold ? 1 : 0; }
 
 static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimbs, const uint32_t *chk, int chklimbs,
                       uint32_t max_curves);
@@ -164,7 +200,13 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
         return fail(ECM_B200_ENODEV, "no usable CUDA device (this engine has no CPU fallback)");
-    Engine *eng = make_engine(nlimbs);
+    // special-form base: shift-and-fold kernels when the base has one of the reference's shapes and the kernel
+    // set covers its length; otherwise (and with ECM_B200_NO_FOLD set) the Montgomery kernels modulo the base
+    Engine *eng = nullptr;
+    int sp_kind = 0; uint32_t sp_k = 0, sp_c = 0;
+    if (chk && !getenv("ECM_B200_NO_FOLD") && special_shape(n, nlimbs, &sp_kind, &sp_k, &sp_c)) eng = make_special_engine(nlimbs, sp_k);
+    const bool fold = eng != nullptr;
+    if (!eng) eng = make_engine(nlimbs);
     if (!eng) return fail(ECM_B200_EINVAL, "modulus too large: kernels are built for up to 2048 bits (64 limbs)");
     ecm_b200_ctx *c = new ecm_b200_ctx();
     c->device = device; c->eng = eng; c->nl = eng->nl; c->max_curves = max_curves;
@@ -180,6 +222,10 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
     uint32_t maxbits_ref = 208; while (maxbits_ref <= bitlen(c->n)) maxbits_ref += 208;
     Big rri = one; for (uint32_t i = 0; i < maxbits_ref; i++) half_mod(rri, c->n);   // R * 2^-MAXBITS mod N
     c->chk = c->n;
+    if (fold) {                                           // plain residues: "R = 1"
+        one.assign(nl, 0); one[0] = 1;
+        r2 = one; r3 = one;
+    }
     if (chk) {                                            // special form: plain residues, R_ref = 1
         rri = one;
         c->chk.assign(nl, 0);
@@ -189,6 +235,8 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
     uint32_t inv = 1; for (int i = 0; i < 5; i++) inv *= 2 - c->n[0] * inv;           // N^-1 mod 2^32
     const uint32_t m0inv = 0u - inv;
     eng->set_params(c->n, one, r2, r3, rri, m0inv);
+    if (fold) eng->set_special(sp_kind, sp_k, sp_c);
+    c->fold = fold;
 
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e_); ecm_b200_destroy(c); return fail(ECM_B200_ECUDA, m); } } while (0)
     CUC(cudaSetDevice(device));

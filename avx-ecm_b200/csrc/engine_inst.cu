@@ -7,6 +7,7 @@
 #endif
 
 namespace ecmb200 {
+inline namespace ECM_VNS {
 
 template <int NL>
 struct EngineT : Engine {
@@ -21,7 +22,12 @@ struct EngineT : Engine {
     void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, uint32_t m0inv) override
     {
         for (int k = 0; k < NL; k++) { P.n[k] = n[k]; P.one[k] = one[k]; P.r2[k] = r2[k]; P.r3[k] = r3[k]; P.rrefinv[k] = rri[k]; }
-        P.m0inv = m0inv;
+        P.m0inv = m0inv; P.kind = 0; P.kbits = 0; P.cval = 0;
+    }
+    void set_special(int kind, uint32_t kbits, uint32_t cval) override { P.kind = kind; P.kbits = kbits; P.cval = cval; }
+    bool serves_special(uint32_t kbits) const override
+    {
+        return ECM_SPECIAL && NL <= 32 && kbits >= 64 && (int)(kbits >> 5) >= SpecialRange<NL>::LOW && (int)(kbits >> 5) < NL;
     }
     const void *params_host() const override { return &P; }
     void set_params_device(const void *d) override { Pg = static_cast<const ModParams<NL> *>(d); }
@@ -94,8 +100,14 @@ struct EngineT : Engine {
     }
 };
 
+}  // inline namespace ECM_VNS
+
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
+#if ECM_SPECIAL
+Engine *CAT(make_engine_sp_, ECM_NL)() { return new EngineT<ECM_NL>(); }
+#else
 Engine *CAT(make_engine_, ECM_NL)() { return new EngineT<ECM_NL>(); }
+#endif
 
 }  // namespace ecmb200

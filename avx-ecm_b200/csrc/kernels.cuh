@@ -9,6 +9,7 @@
 #include "modinv.cuh"
 
 namespace ecmb200 {
+inline namespace ECM_VNS {
 
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int NSMEM_S1 = 5;      // stage-1 slots kept in shared memory (s1,d1,s2,d2,sp); the 8 point slots stay in global
@@ -530,4 +531,5 @@ __global__ void k_s2_collect(const uint32_t *state2, uint32_t cap2, const uint8_
     fail_out[first + c] = inv_fail[c];
 }
 
+}  // inline namespace ECM_VNS
 }  // namespace ecmb200

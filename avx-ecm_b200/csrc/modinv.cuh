@@ -7,6 +7,7 @@
 #include "mp.cuh"
 
 namespace ecmb200 {
+inline namespace ECM_VNS {
 
 // in : x in [0,N)
 // out: g = gcd(x,N) (g = N for x = 0); if g == 1, inv = x^-1 mod N in [0,N).  Returns g == 1.
@@ -100,4 +101,5 @@ __device__ __noinline__ bool mod_inverse(uint32_t (&inv)[NL], uint32_t (&g)[NL],
     return ok;
 }
 
+}  // inline namespace ECM_VNS
 }  // namespace ecmb200

@@ -13,8 +13,23 @@
 // division by 2^32 swaps the roles: T/2^32 = O + E[1] + (E>>64)*2^32.
 #pragma once
 #include <stdint.h>
+#include "special_fold.hpp"
+
+// Kernel variant of this translation unit.  ECM_SPECIAL = 1: every modular product is a plain double-length
+// product followed by the shift-and-fold reduction of special_fold.hpp (bases 2^k-c, 2^k+1; residues are
+// plain, i.e. "Montgomery form with R = 1": one = r2 = r3 = 1).  The variants live in different inline
+// namespaces so that their kernels and engine classes are distinct symbols in libecm_b200.so.
+#ifndef ECM_SPECIAL
+#define ECM_SPECIAL 0
+#endif
+#if ECM_SPECIAL
+#define ECM_VNS sp
+#else
+#define ECM_VNS gen
+#endif
 
 namespace ecmb200 {
+inline namespace ECM_VNS {
 
 // ---- carry-chain primitives (CC flag lives between consecutive asm volatile statements) ----
 __device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
@@ -42,6 +57,9 @@ struct ModParams {
     uint32_t rrefinv[NL];// (2^-MAXBITS_ref) * R mod N : Montgomery form of the reference's R^-1, used
                          // only on the inversion-failure path (see vm.cuh op INV)
     uint32_t m0inv;      // -N^-1 mod 2^32   (monty.vrho, main.c:637-640)
+    // special-form base (only read by the ECM_SPECIAL kernels): N = 2^kbits - cval (kind > 0) or 2^kbits + 1 (kind < 0)
+    int32_t kind;
+    uint32_t kbits, cval;
 };
 
 template <int NL> struct MontW { static constexpr int W = (NL % 2 == 0) ? NL + 2 : NL + 3; };
@@ -68,11 +86,57 @@ __device__ __forceinline__ void mad_row(uint32_t (&acc)[W], const XT &x, uint32_
     }
 }
 
+// T = a*b, all 2*NL limbs: the rows of mont_mul without the reduction half.  The low word of each row is
+// final (nothing is added below it afterwards) and is retired to T[i]; the window that is left after NL
+// rows is the high half.
+template <int NL>
+__device__ __forceinline__ void full_mul(uint32_t (&T)[2 * NL], const uint32_t (&a)[NL], const uint32_t (&b)[NL])
+{
+    constexpr int W = MontW<NL>::W;
+    uint32_t X[W], Y[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) { X[k] = 0; Y[k] = 0; }
+    auto row = [&](uint32_t (&Eo)[W], uint32_t (&Oo)[W], uint32_t bi, uint32_t &low) {
+        uint32_t e1 = Eo[1];
+#pragma unroll
+        for (int k = 0; k < W - 2; k++) Eo[k] = Eo[k + 2];
+        Eo[W - 2] = 0; Eo[W - 1] = 0;
+        add_cc(Oo[0], e1);
+        if (NL > 1) mad_row<NL, W, 1, true>(Eo, a, bi);
+        else { addc_cc(Eo[0], 0); addc(Eo[1], 0); }
+        mad_row<NL, W, 0, false>(Oo, a, bi);
+        low = Oo[0];
+    };
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+        if ((i & 1) == 0) row(X, Y, b[i], T[i]); else row(Y, X, b[i], T[i]);
+    }
+    uint32_t (&E)[W] = (NL % 2 == 0) ? X : Y;
+    uint32_t (&O)[W] = (NL % 2 == 0) ? Y : X;
+    T[NL] = add3_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 1; k < NL - 1; k++) T[NL + k] = addc3_cc(E[k + 1], O[k]);
+    T[2 * NL - 1] = addc3(E[NL], O[NL - 1]);
+}
+
+// r = a*b mod N for a special-form N (P.kind/kbits/cval), canonical
+template <int NL>
+__device__ __forceinline__ void special_mul(uint32_t (&r)[NL], const uint32_t (&a)[NL], const uint32_t (&b)[NL],
+                                            const ModParams<NL> &P)
+{
+    uint32_t T[2 * NL];
+    full_mul<NL>(T, a, b);
+    special_fold<NL>(r, T, P.kbits, P.kind, P.cval);
+}
+
 // r = a*b*R^-1 mod N, canonical.  a,b canonical (< N).
 template <int NL>
 __device__ __forceinline__ void mont_mul(uint32_t (&r)[NL], const uint32_t (&a)[NL], const uint32_t (&b)[NL],
                                          const ModParams<NL> &P)
 {
+#if ECM_SPECIAL
+    special_mul<NL>(r, a, b, P);
+#else
     constexpr int W = MontW<NL>::W;
     uint32_t X[W], Y[W];
 #pragma unroll
@@ -116,6 +180,7 @@ __device__ __forceinline__ void mont_mul(uint32_t (&r)[NL], const uint32_t (&a)[
     bool take = (nb != 0xffffffffu);
 #pragma unroll
     for (int k = 0; k < NL; k++) r[k] = take ? d[k] : t[k];
+#endif
 }
 
 // Two independent products at once, rows interleaved: (r0,r1) = (a0*b0, a1*b1) * R^-1 mod N.
@@ -127,6 +192,16 @@ __device__ __forceinline__ void mont_mul2(uint32_t (&r0)[NL], const uint32_t (&a
                                           uint32_t (&r1)[NL], const uint32_t (&a1)[NL], const uint32_t (&b1)[NL],
                                           const ModParams<NL> &P)
 {
+#if ECM_SPECIAL
+    {
+        uint32_t t0[NL];                                   // r0 may alias a1/b1
+        special_mul<NL>(t0, a0, b0, P);
+        special_mul<NL>(r1, a1, b1, P);
+#pragma unroll
+        for (int k = 0; k < NL; k++) r0[k] = t0[k];
+        return;
+    }
+#endif
     constexpr int W = MontW<NL>::W;
     uint32_t X0[W], Y0[W], X1[W], Y1[W];
 #pragma unroll
@@ -310,7 +385,7 @@ template <int NL> struct UseSqr { static constexpr bool value = (NL >= 20 && NL 
 template <int NL>
 __device__ __forceinline__ void mont_sqr(uint32_t (&r)[NL], const uint32_t (&a)[NL], const ModParams<NL> &P)
 {
-    if (!UseSqr<NL>::value) { mont_mul<NL>(r, a, a, P); return; }
+    if (!UseSqr<NL>::value || ECM_SPECIAL) { mont_mul<NL>(r, a, a, P); return; }
     uint32_t rr[1][NL], aa[1][NL];
 #pragma unroll
     for (int k = 0; k < NL; k++) aa[0][k] = a[k];
@@ -444,4 +519,5 @@ __device__ __forceinline__ void mod_sub_stream(const AT &a, const BT &b, const M
     for (int k = 1; k < NL; k++) { v = (k == NL - 1) ? addc3(t[k], P.n[k] & bo) : addc3_cc(t[k], P.n[k] & bo); put(k, v); }
 }
 
+}  // inline namespace ECM_VNS
 }  // namespace ecmb200

@@ -19,6 +19,7 @@
 #include "mp.cuh"
 
 namespace ecmb200 {
+inline namespace ECM_VNS {
 
 // ---- micro-ops --------------------------------------------------------------------------
 enum : uint32_t { U_MUL = 0, U_SQR = 1, U_ADD = 2, U_SUB = 3, U_ADDSUB = 4, U_COPY = 5, U_MUL2 = 6, U_END = 15 };
@@ -238,4 +239,5 @@ __device__ __forceinline__ void exec_uop(const SlotsT &S, uint32_t u, uint32_t p
     }
 }
 
+}  // inline namespace ECM_VNS
 }  // namespace ecmb200

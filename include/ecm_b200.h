@@ -47,6 +47,10 @@ int ecm_b200_create(ecm_b200_ctx **out, int device, const uint32_t *n, int nlimb
  * Detecting the form and removing algebraic factors is the caller's job (main.c:405-457).    */
 int ecm_b200_create_special(ecm_b200_ctx **out, int device, const uint32_t *base, int baselimbs,
                             const uint32_t *n, int nlimbs, uint32_t max_curves);
+/* 1 when the context computes with the shift-and-fold kernels (base of the shape 2^k-c, c < 2^31, or 2^k+1,
+ * 64 <= k <= 1023, and kernels compiled for its length), 0 when it uses Montgomery products.  Results are
+ * identical either way; the environment variable ECM_B200_NO_FOLD forces the Montgomery kernels.        */
+int ecm_b200_uses_fold(const ecm_b200_ctx *ctx);
 void ecm_b200_destroy(ecm_b200_ctx *ctx);
 const char *ecm_b200_last_error(void);
 /* number of 32-bit limbs the engine computes with (>= nlimbs of N; kernels exist for a fixed set) */
