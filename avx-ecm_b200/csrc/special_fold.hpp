@@ -45,7 +45,14 @@ inline uint32_t sf_madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_
 #endif
 
 // limb of (x >> s) from two neighbouring limbs
-ECM_SF_HD uint32_t sf_shr(uint32_t lo, uint32_t hi, uint32_t s) { return s ? (lo >> s) | (hi << (32 - s)) : lo; }
+ECM_SF_HD uint32_t sf_shr(uint32_t lo, uint32_t hi, uint32_t s)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, s);                         // one SHF; s = 0 returns lo
+#else
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
 
 // kind > 0: M = 2^k - c; kind < 0: M = 2^k + 1.  T < M^2 (2*NL limbs), 32*NL > k >= 64, c < 2^31.
 // About 6 single-issue instructions per limb (4 for 2^k+1), every one a link of a carry chain.
