@@ -46,7 +46,7 @@ struct S1Cfg {
     static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
     // dual-product micro-ops (NL <= 16) want ~150 registers: at most 384 threads per block.  The fold kernels
     // run their two products one after the other (~110 registers) and are latency-bound: 512 threads
-    static constexpr int cap = (NL <= 16) ? (ECM_SPECIAL ? 512 : 384) : 768;
+    static constexpr int cap = (NL <= 16) ? (ECM_SPECIAL ? (NL <= 10 ? 768 : NL <= 13 ? 640 : 512) : 384) : 768;
     static constexpr int STRIDE = fit > cap ? cap : fit;          // max threads per block = lane stride
     static constexpr int smem = per_thread * STRIDE;
 };
