@@ -53,6 +53,8 @@ def lib():
         "ecm_b200_build_curves": (c.c_int, [vp, c.c_uint32, u64p]),
         "ecm_b200_load_curves": (c.c_int, [vp, c.c_uint32, u32p, u32p]),
         "ecm_b200_stage1": (c.c_int, [vp, c.c_uint64]),
+        "ecm_b200_stage1_ranges": (c.c_int, [c.c_uint64, c.POINTER(c.c_uint32)]),
+        "ecm_b200_stage1_range": (c.c_int, [vp, c.c_uint64, c.c_uint32, c.POINTER(c.c_uint64)]),
         "ecm_b200_stage1_begin": (c.c_int, [vp, c.c_uint64]),
         "ecm_b200_stage1_step": (c.c_int, [vp, c.c_uint32, c.POINTER(c.c_int)]),
         "ecm_b200_stage1_launches": (c.c_int, [vp, u32p, u32p]),
@@ -82,7 +84,7 @@ def lib():
 
 
 EXPORTS = ["ecm_b200_create", "ecm_b200_create_special", "ecm_b200_uses_fold", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
-           "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
+           "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_ranges", "ecm_b200_stage1_range", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
            "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_stage1_progress", "ecm_b200_flush_l2", "ecm_b200_timer", "ecm_b200_read_stage1", "ecm_b200_stage2",
            "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_stage2_program", "ecm_b200_pair", "ecm_b200_stage2_params",
            "ecm_b200_fieldop", "ecm_b200_launch_count", "ecm_b200_last_timing", "ecm_b200_measure_imad_peak"]
@@ -171,6 +173,12 @@ class EcmContext:
         _check(lib().ecm_b200_stage1(self._h, b1))
         self.b1 = b1
 
+    def stage1_range(self, b1, r):
+        """One 1e8 prime range of stage 1 (ecm.c:1207-1234); -> the last prime used (the B1 of the checkpoint line)."""
+        last = ctypes.c_uint64()
+        _check(lib().ecm_b200_stage1_range(self._h, b1, r, ctypes.byref(last)))
+        return last.value
+
     def stage1_begin(self, b1):
         _check(lib().ecm_b200_stage1_begin(self._h, b1))
         self.b1 = b1
@@ -254,6 +262,13 @@ def measure_imad_peak(device=0):
     r, clk = ctypes.c_double(), ctypes.c_double()
     _check(lib().ecm_b200_measure_imad_peak(device, ctypes.byref(r), ctypes.byref(clk)))
     return r.value, clk.value
+
+
+def stage1_ranges(b1):
+    """Number of prime ranges the reference (and ecm_b200_stage1) splits stage 1 into: ceil(B1 / 1e8)."""
+    n = ctypes.c_uint32()
+    _check(lib().ecm_b200_stage1_ranges(b1, ctypes.byref(n)))
+    return n.value
 
 
 def plan_stage1(b1):

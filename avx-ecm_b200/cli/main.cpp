@@ -34,6 +34,9 @@ struct Shard {
     std::vector<uint64_t> sigma;
     std::vector<uint32_t> X, Z, G1, G2;
     std::vector<uint8_t> f1, f2;
+    // state after every stage-1 prime range but the last (what the reference appends to checkpoint.txt)
+    struct Checkpoint { uint64_t last_prime; std::vector<uint32_t> X, Z, G; std::vector<uint8_t> f; };
+    std::vector<Checkpoint> ckpt;
     int limbs = 0;
     double t_build = 0, t_s1 = 0, t_s2 = 0;
     std::string error;
@@ -54,7 +57,18 @@ static void run_shard(Shard *s, const std::vector<uint32_t> *n32, const std::vec
     double t0 = now();
     int rc = ecm_b200_build_curves(ctx, s->count, s->sigma.data());
     s->t_build = now() - t0; t0 = now();
-    if (!rc) rc = ecm_b200_stage1(ctx, b1);
+    uint32_t nranges = 1;
+    if (!rc) rc = ecm_b200_stage1_ranges(b1, &nranges);
+    if (!rc && nranges <= 1) rc = ecm_b200_stage1(ctx, b1);
+    for (uint32_t r = 0; !rc && nranges > 1 && r < nranges; r++) {           // vececm's range loop, ecm.c:1207-1311
+        uint64_t last = 0;
+        rc = ecm_b200_stage1_range(ctx, b1, r, &last);
+        if (rc || r + 1 == nranges) break;
+        Shard::Checkpoint c;
+        c.last_prime = last; c.X.resize(words); c.Z.resize(words); c.G.resize(words); c.f.resize(s->count);
+        rc = ecm_b200_read_stage1(ctx, c.X.data(), c.Z.data(), c.f.data(), c.G.data());
+        s->ckpt.push_back(std::move(c));
+    }
     if (!rc) rc = ecm_b200_read_stage1(ctx, s->X.data(), s->Z.data(), s->f1.data(), s->G1.data());
     s->t_s1 = now() - t0; t0 = now();
     if (!rc && do2) {
@@ -170,10 +184,27 @@ int main(int argc, char **argv)
     printf("Building curves took %1.4f seconds.\n", tb);
     printf("Stage 1 took %1.4f seconds\n", ts1);
 
-    // save_b1.txt, in sigma order = batch/thread/lane order of the reference with threads=1
     int found = 0;
-    FILE *save = fopen("save_b1.txt", "a");
     FILE *res = fopen("ecm_results.txt", "a");
+    // checkpoint.txt: one block of lines per finished prime range, B1 = the last prime used (ecm.c:1237-1311)
+    for (size_t r = 0; r < shards[0].ckpt.size(); r++) {
+        FILE *ck = fopen("checkpoint.txt", "a");
+        if (!ck) { printf("could not open checkpoint.txt for appending, Stage 1 data will not be saved\n"); break; }
+        printf("Saving checkpoint after p=%" PRIu64 "\n", shards[0].ckpt[r].last_prime);
+        for (auto &s : shards) {
+            const Shard::Checkpoint &c = s.ckpt[r];
+            for (uint32_t i = 0; i < s.count; i++) {
+                limbs_to_mpz(x, c.X, s.limbs, s.count, i);
+                limbs_to_mpz(z, c.Z, s.limbs, s.count, i);
+                if (c.f[i]) { limbs_to_mpz(f, c.G, s.limbs, s.count, i); report(res, f, 1, c.last_prime, s.first + i, s.sigma[i]); found = 1; }
+                fprintf(ck, "METHOD=ECM; SIGMA=%" PRIu64 "; B1=%" PRIu64 "; ", s.sigma[i], c.last_prime);
+                gmp_fprintf(ck, "N=0x%Zx; X=0x%Zx; Z=0x%Zx; PROGRAM=AVX-ECM;\n", N, x, z);
+            }
+        }
+        fclose(ck);
+    }
+    // save_b1.txt, in sigma order = batch/thread/lane order of the reference with threads=1
+    FILE *save = fopen("save_b1.txt", "a");
     if (!save) printf("could not open save_b1.txt for appending, Stage 1 data will not be saved\n");
     for (auto &s : shards) {
         for (uint32_t i = 0; i < s.count; i++) {

@@ -150,6 +150,8 @@ struct ecm_b200_ctx {
     // stage-1 schedule
     uint32_t chunk_len = 0; uint64_t total_items = 0, next_item = 0; uint32_t launches_total = 0, launches_issued = 0;
     int p_slot = 0;             // physical point slot holding P
+    uint64_t seg_begin = 0, seg_len = 0; int seg_final_slot = 0; bool seg_last = true, seg_done = false;   // op-stream segment being run
+    uint32_t next_range = 0;    // range-by-range stage 1: the next prime range to run
     bool have_curves = false, stage1_done = false;
     float last_ms = 0; uint32_t last_launches = 0;
     // stage 2
@@ -313,7 +315,7 @@ static int set_count(ecm_b200_ctx *c, uint32_t count)
     if (count < 1 || count > c->max_curves) return fail(ECM_B200_EINVAL, "count exceeds the context's max_curves");
     c->count = count;
     c->groups = (count + c->T - 1) / c->T;
-    c->have_curves = true; c->stage1_done = false; c->p_slot = 0;
+    c->have_curves = true; c->stage1_done = false; c->p_slot = 0; c->next_range = 0; c->seg_done = false;
     c->total_items = c->next_item = 0; c->launches_total = c->launches_issued = 0;
     return ECM_B200_OK;
 }
@@ -355,13 +357,14 @@ int ecm_b200_build_curves(ecm_b200_ctx *c, uint32_t count, const uint64_t *sigma
     return ECM_B200_OK;
 }
 
-int ecm_b200_stage1_begin(ecm_b200_ctx *c, uint64_t b1)
+// plan for b1 on the device; the schedule of one segment [begin, end) of its op stream
+static int stage1_prepare(ecm_b200_ctx *c, uint64_t b1)
 {
     if (!c) return fail(ECM_B200_EINVAL, "null context");
     if (!c->have_curves) return fail(ECM_B200_ESTATE, "no curves loaded");
-    // one prime range only: beyond 1e8 the reference restarts ecm_stage1 per range (repeating the powers of
-    // two and skipping each range's first prime, ecm.c:1209-1234,1815-1824); that quirk is not reproduced
-    if (b1 < 2 || b1 > 100000000ull) return fail(ECM_B200_EINVAL, "B1 out of range (2 .. 1e8)");
+    // beyond 1e8 the stream follows the reference's range-by-range driver, quirks included (plan.cpp); the cap keeps
+    // p*p inside 64 bits (ecm.c:1832) and the op stream (about 2 bytes per unit of B1) inside host memory
+    if (b1 < 2 || b1 > 2000000000ull) return fail(ECM_B200_EINVAL, "B1 out of range (2 .. 2e9)");
     CU(cudaSetDevice(c->device));
     if (c->plan.b1 != b1) { plan_stage1(b1, c->plan); c->plan_on_device = false; }
     if (!c->plan_on_device) {
@@ -374,15 +377,21 @@ int ecm_b200_stage1_begin(ecm_b200_ctx *c, uint64_t b1)
         c->plan_on_device = true;
     }
     if (c->stage1_done) return fail(ECM_B200_ESTATE, "stage 1 already run on this batch");
+    return ECM_B200_OK;
+}
+
+static int stage1_segment(ecm_b200_ctx *c, uint64_t begin, uint64_t end, int final_slot, bool last)
+{
     // Schedule: an item is (group of THREADS curves, chunk of the op stream).  Items are ordered
     // chunk-major and a launch takes a run of consecutive items, at most one per SM; because a run
     // is never longer than the number of groups, item (g, c-1) is always in an earlier launch.
-    const uint64_t nops = c->plan.ops.size();
+    const uint64_t nops = end - begin;
     uint32_t chunk = 32768;
     if (c->groups > (uint32_t)c->num_sms) {
         // several waves: finer chunks keep the last partial launch small
         chunk = 8192;
     }
+    c->seg_begin = begin; c->seg_len = nops; c->seg_final_slot = final_slot; c->seg_last = last;
     c->chunk_len = chunk;
     const uint64_t nchunks = (nops + chunk - 1) / chunk;
     c->total_items = nchunks * c->groups;
@@ -391,33 +400,70 @@ int ecm_b200_stage1_begin(ecm_b200_ctx *c, uint64_t b1)
     c->launches_total = (uint32_t)((c->total_items + per - 1) / per);
     c->launches_issued = 0;
     c->last_launches = 0;
+    c->seg_done = false;
     CU(cudaEventRecord(c->ev0, c->stream));
     if (c->total_items == 0) {                    // nothing to do (B1 = 2): the point is unchanged
-        c->stage1_done = true;
-        c->p_slot = c->plan.final_slot;
+        c->seg_done = true;
+        c->stage1_done = last;
+        c->p_slot = final_slot;
         CU(cudaEventRecord(c->ev1, c->stream));
     }
     return ECM_B200_OK;
 }
 
+int ecm_b200_stage1_begin(ecm_b200_ctx *c, uint64_t b1)
+{
+    int rc = stage1_prepare(c, b1); if (rc) return rc;
+    if (c->next_range != 0) return fail(ECM_B200_ESTATE, "stage 1 was started range by range on this batch");
+    return stage1_segment(c, 0, c->plan.ops.size(), c->plan.final_slot, true);
+}
+
+int ecm_b200_stage1_ranges(uint64_t b1, uint32_t *count)
+{
+    if (!count || b1 < 2) return fail(ECM_B200_EINVAL, "bad argument");
+    const uint64_t w = stage1_prime_range();
+    *count = (uint32_t)((b1 + w - 1) / w);
+    return ECM_B200_OK;
+}
+
+// One prime range of stage 1 (ecm.c:1207-1234), run to completion; ranges must be taken in order.  Afterwards
+// read_stage1 returns the state the reference writes to checkpoint.txt (ecm.c:1237-1311) -- or, after the last
+// range, the stage-1 result.
+int ecm_b200_stage1_range(ecm_b200_ctx *c, uint64_t b1, uint32_t range, uint64_t *last_prime)
+{
+    int rc = stage1_prepare(c, b1); if (rc) return rc;
+    const auto &re = c->plan.range_end;
+    if (range >= re.size()) return fail(ECM_B200_EINVAL, "no such prime range for this B1");
+    if (range != c->next_range) return fail(ECM_B200_ESTATE, "prime ranges must be run in order, starting from freshly built curves");
+    const uint64_t begin = range ? re[range - 1].ops : 0;
+    const bool last = range + 1 == re.size();
+    rc = stage1_segment(c, begin, last ? c->plan.ops.size() : re[range].ops, re[range].slot, last); if (rc) return rc;
+    int done = 0;
+    rc = ecm_b200_stage1_step(c, 0xffffffffu, &done); if (rc) return rc;
+    c->next_range = range + 1;
+    if (last_prime) *last_prime = re[range].last_prime;
+    return ecm_b200_sync(c);
+}
+
 int ecm_b200_stage1_step(ecm_b200_ctx *c, uint32_t max_launches, int *done)
 {
     if (!c) return fail(ECM_B200_EINVAL, "null context");
-    if (c->total_items == 0 && c->stage1_done) { if (done) *done = 1; return ECM_B200_OK; }   // empty op stream (B1 = 2)
+    if (c->total_items == 0 && c->seg_done) { if (done) *done = 1; return ECM_B200_OK; }   // empty op stream (B1 = 2)
     if (c->total_items == 0) return fail(ECM_B200_ESTATE, "stage1_begin not called");
     CU(cudaSetDevice(c->device));
     const uint32_t per = std::min<uint32_t>(c->groups, (uint32_t)c->num_sms);
     uint32_t n = 0;
     while (c->next_item < c->total_items && n < max_launches) {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(per, c->total_items - c->next_item);
-        c->eng->stage1(c->stream, blocks, c->T, c->d_state, c->d_ops, c->plan.ops.size(), c->chunk_len, c->groups, c->next_item);
+        c->eng->stage1(c->stream, blocks, c->T, c->d_state, c->d_ops + c->seg_begin, c->seg_len, c->chunk_len, c->groups, c->next_item);
         c->next_item += blocks; c->launches_issued++; c->last_launches++; n++;
     }
     CU(cudaGetLastError());
     const bool fin = c->next_item >= c->total_items;
-    if (fin && !c->stage1_done) {
-        c->stage1_done = true;
-        c->p_slot = c->plan.final_slot;
+    if (fin && !c->seg_done) {
+        c->seg_done = true;
+        c->stage1_done = c->seg_last;
+        c->p_slot = c->seg_final_slot;
         CU(cudaEventRecord(c->ev1, c->stream));
     }
     if (done) *done = fin ? 1 : 0;
@@ -437,7 +483,7 @@ int ecm_b200_stage1_progress(const ecm_b200_ctx *c, double *fraction)
     if (!c) return fail(ECM_B200_EINVAL, "null context");
     // every item covers chunk_len ops except those of the last chunk
     if (fraction) {
-        const uint64_t nops = c->plan.ops.size();
+        const uint64_t nops = c->seg_len;
         if (c->total_items == 0 || nops == 0) { *fraction = 0; return ECM_B200_OK; }
         const uint64_t full_chunks = c->next_item / c->groups, rest = c->next_item % c->groups;
         const uint64_t nchunks = c->total_items / c->groups;

@@ -2,6 +2,7 @@
 // reference functions cited at each routine so that the device executes the same sequence of
 // field operations (SURVEY facts 2, 3, 8 and Appendices A/B).
 #include "plan.hpp"
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -128,46 +129,69 @@ enum { LA = 0, LB = 1, LC = 2, LT = 3 };
 enum { M_DBL = 0, M_INIT = 1, M_C3 = 2, M_C4 = 3, M_C5 = 4, M_C9 = 5, M_FINAL = 6, M_NOP = 7 };
 }  // namespace
 
+// The reference runs stage 1 once per range of kStage1Range = 1e8 primes-by-value (vececm, ecm.c:1207-1234), and
+// every call of ecm_stage1 (ecm.c:1806-1854) (a) repeats the doublings for q = 2,4,.. < B1 and (b) starts at
+// PRIMES[1] of the range it was handed.  For B1 <= 1e8 that is one call that skips the prime 2 (covered by the
+// doublings).  Beyond, the stream below reproduces the quirks: the doublings are emitted once per range and the
+// first prime of every later range (100000007, 200000033, ...) is left out.
+uint64_t stage1_prime_range()
+{
+    // PRIME_RANGE of the reference (main.c:585).  ECM_B200_S1_RANGE is a test hook: small ranges let the
+    // tests drive the range-by-range path (checkpoints, repeated doublings, skipped primes) at small B1.
+    if (const char *e = getenv("ECM_B200_S1_RANGE")) { const uint64_t v = strtoull(e, nullptr, 10); if (v >= 16) return v; }
+    return 100000000ull;
+}
+
 void plan_stage1(uint64_t b1, Stage1Plan &plan)
 {
     plan = Stage1Plan();
     plan.b1 = b1;
     Emitter em{plan, {1, 2, 3, 0}, 0};
-    // powers of two: one doubling per q = 2,4,8,... < B1 (ecm.c:1815-1822)
-    for (uint64_t q = 2; q < b1; q *= 2) {
-        em.make_role(LT, em.pslot);
-        em.put(M_DBL);
-        plan.ptdups++;
-    }
-    // odd primes p < B1, prac(p) repeated while p^k * p < B1 (ecm.c:1824-1832)
-    std::vector<uint64_t> primes = primes_in_range(3, b1);
-    for (uint64_t p : primes) {
-        uint64_t c = 1;
-        do {
-            const double v = kPracV[best_multiplier(p)];
-            em.make_role(LB, em.pslot);           // B = P (no copy), C = copy, A = 2P
-            em.put(M_INIT);
+    const uint64_t kStage1Range = stage1_prime_range();
+    for (uint64_t lo = 0; lo < b1; lo += kStage1Range) {
+        // powers of two: one doubling per q = 2,4,8,... < B1 (ecm.c:1815-1822)
+        for (uint64_t q = 2; q < b1; q *= 2) {
+            em.make_role(LT, em.pslot);
+            em.put(M_DBL);
             plan.ptdups++;
-            walk(p, v, [&](bool swapped, Rule rule) {
-                if (swapped) std::swap(em.slot[LA], em.slot[LB]);
-                switch (rule) {
-                case R3: {
-                    em.put(M_C3);
-                    int oldB = em.slot[LB];
-                    em.slot[LB] = em.slot[LT]; em.slot[LT] = em.slot[LC]; em.slot[LC] = oldB;
-                    plan.ptadds++;
-                    break;
-                }
-                case R4: em.put(M_C4); plan.ptadds++; plan.ptdups++; break;
-                case R5: em.put(M_C5); plan.ptadds++; plan.ptdups++; break;
-                case R9: em.put(M_C9); plan.ptadds++; plan.ptdups++; break;
-                }
-            });
-            em.put(M_FINAL);
-            plan.ptadds++;
-            em.pslot = em.slot[LT];
-            c *= p;
-        } while (c * p < b1);
+        }
+        // the primes of this range below B1 without the first one, prac(p) repeated while p^k * p < B1 (ecm.c:1824-1832)
+        std::vector<uint64_t> primes = primes_in_range(lo, std::min(b1, lo + kStage1Range));
+        uint64_t last = 0;
+        for (size_t i = 1; i < primes.size(); i++) {
+            const uint64_t p = primes[i];
+            last = p;
+            uint64_t c = 1;
+            do {
+                const double v = kPracV[best_multiplier(p)];
+                em.make_role(LB, em.pslot);           // B = P (no copy), C = copy, A = 2P
+                em.put(M_INIT);
+                plan.ptdups++;
+                walk(p, v, [&](bool swapped, Rule rule) {
+                    if (swapped) std::swap(em.slot[LA], em.slot[LB]);
+                    switch (rule) {
+                    case R3: {
+                        em.put(M_C3);
+                        int oldB = em.slot[LB];
+                        em.slot[LB] = em.slot[LT]; em.slot[LT] = em.slot[LC]; em.slot[LC] = oldB;
+                        plan.ptadds++;
+                        break;
+                    }
+                    case R4: em.put(M_C4); plan.ptadds++; plan.ptdups++; break;
+                    case R5: em.put(M_C5); plan.ptadds++; plan.ptdups++; break;
+                    case R9: em.put(M_C9); plan.ptadds++; plan.ptdups++; break;
+                    }
+                });
+                em.put(M_FINAL);
+                plan.ptadds++;
+                em.pslot = em.slot[LT];
+                c *= p;
+            } while (c * p < b1);
+        }
+        // where checkpoint.txt would be written (ecm.c:1237-1311): stream position, slot of P, last prime done;
+        // padded so that the next range starts on a 16-byte boundary of the stream
+        if (lo + kStage1Range < b1) while (plan.ops.size() % 16) plan.ops.push_back(M_NOP);
+        plan.range_end.push_back({(uint64_t)plan.ops.size(), em.pslot, last});
     }
     plan.n_ops = plan.ops.size();
     plan.final_slot = em.pslot;

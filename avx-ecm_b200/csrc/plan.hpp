@@ -21,7 +21,12 @@ struct Stage1Plan {
     uint64_t n_ops = 0;         // unpadded length
     uint64_t ptadds = 0, ptdups = 0;
     int final_slot = 0;         // physical point slot that holds P after the stream
+    // one entry per 1e8 prime range (ecm.c:1207-1234): ops emitted up to its end, slot of P there, last prime used
+    struct RangeEnd { uint64_t ops; int slot; uint64_t last_prime; };
+    std::vector<RangeEnd> range_end;
 };
+// width of the prime ranges stage 1 is run in (1e8 like the reference; see plan.cpp)
+uint64_t stage1_prime_range();
 // P starts in physical point slot 0.
 void plan_stage1(uint64_t b1, Stage1Plan &plan);
 

@@ -68,6 +68,14 @@ int ecm_b200_load_curves(ecm_b200_ctx *ctx, uint32_t count, const uint32_t *x, c
  * Multiplies every curve's point by 2^e * prod p^k for p^k < B1.  The PRAC chains are planned on
  * the host (ecm_b200_plan_stage1) and cached in the context.                                   */
 int ecm_b200_stage1(ecm_b200_ctx *ctx, uint64_t b1);
+/* B1 above 1e8: the reference runs ecm_stage1 once per range of 1e8 primes-by-value and appends the
+ * intermediate points to checkpoint.txt after every range but the last (vececm, ecm.c:1207-1311).  Every
+ * such call repeats the doublings for the powers of two and starts at the second prime of its range
+ * (ecm.c:1815-1824); ecm_b200_stage1 reproduces exactly that in one go (2 <= B1 <= 2e9).  To write the
+ * checkpoints, run the ranges one at a time, in order, on freshly built curves: after range r (not the
+ * last) ecm_b200_read_stage1 returns what the reference saves, with *last_prime the B1 it prints there.  */
+int ecm_b200_stage1_ranges(uint64_t b1, uint32_t *count);
+int ecm_b200_stage1_range(ecm_b200_ctx *ctx, uint64_t b1, uint32_t range, uint64_t *last_prime);
 /* Asynchronous form: enqueue at most max_launches kernel launches of the stage-1 schedule and
  * return; *done is set to 1 when the whole stage has been enqueued.  Used for time slicing.   */
 int ecm_b200_stage1_begin(ecm_b200_ctx *ctx, uint64_t b1);

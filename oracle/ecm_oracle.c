@@ -315,6 +315,33 @@ static void ecm_stage1(owork *w, opt *P, uint64_t b1, const uint64_t *primes, ui
     }
 }
 
+/* The stage-1 driver loop of vececm(), ecm.c:1134-1140 and 1207-1234: primes come in ranges of PRIME_RANGE = 1e8
+ * and ecm_stage1 is called once per range with the global PRIMES array replaced.  Beyond the first range this
+ * has two visible consequences that a bit-exact engine has to copy: every call repeats the doublings for
+ * q = 2,4,.. < B1 (ecm.c:1815-1822), and every call starts at PRIMES[1], so the first prime of each later range
+ * (100000007, 200000033, ...) is never used.  stop_after_ranges > 0 stops early: the state the reference writes
+ * to checkpoint.txt after that many ranges (ecm.c:1237-1311).                                                  */
+static uint64_t STAGE1_PRIME_RANGE = 100000000ULL;      /* PRIME_RANGE, main.c:585 */
+/* test hook: small ranges exercise the range-by-range driver at small B1 (the 1e8 value is pinned by the golden
+ * vector syn206_b1_1.1e8_two_stage1_ranges) */
+void oracle_set_prime_range(uint64_t r) { STAGE1_PRIME_RANGE = r ? r : 100000000ULL; }
+static void stage1_all_ranges(owork *w, opt *P, uint64_t b1, uint64_t b2, int stop_after_ranges)
+{
+    uint64_t p, rangemin = 0, rangemax, nump, *primes;
+    int done = 0;
+    rangemax = (b2 + 1000 < STAGE1_PRIME_RANGE) ? b2 + 1000 : STAGE1_PRIME_RANGE;
+    for (p = 0; p < b1; p += STAGE1_PRIME_RANGE) {
+        if (p >= rangemax) {
+            rangemin = rangemax;
+            rangemax = (b2 + 1000 < rangemin + STAGE1_PRIME_RANGE) ? b2 + 1000 : rangemin + STAGE1_PRIME_RANGE;
+        }
+        primes = sieve_range(rangemin, rangemax, &nump);
+        ecm_stage1(w, P, b1, primes, nump);
+        free(primes);
+        if (stop_after_ranges > 0 && ++done == stop_after_ranges) break;
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* stage 2                                                             */
 /* ------------------------------------------------------------------ */
@@ -680,6 +707,9 @@ int oracle_build_curve(const char *n_hex, uint64_t sigma, char *x_hex, char *s_h
  *  f2_dec      : stage-2 factor ("0" if none)    (ecm.c:1485-1497)
  *  counters[8] : s1 ptadds, s1 ptdups, s2 ptadds, s2 numinv, s2 paired, pairmap steps, found_inv, last amin
  * do_stage2 follows main.c:543-552 (b2 <= b1 disables stage 2).               */
+static int g_stop_after_ranges = 0;       /* oracle_set_checkpoint(): stop stage 1 after that many prime ranges */
+void oracle_set_checkpoint(int ranges) { g_stop_after_ranges = ranges; }
+
 static int ecm_curve(const char *n_hex, const char *m_hex, uint64_t b1, uint64_t b2, uint64_t sigma,
     char *x_hex, char *z_hex, char *f1_dec, char *acc_hex, char *f2_dec, uint32_t *counters)
 {
@@ -693,9 +723,7 @@ static int ecm_curve(const char *n_hex, const char *m_hex, uint64_t b1, uint64_t
     build_one_curve(w, P.X, P.Z, A, sigma);
     mpz_set(w->s, A);
 
-    primes = sieve_range(0, b1 + 1000, &nump);
-    ecm_stage1(w, &P, b1, primes, nump);
-    free(primes);
+    stage1_all_ranges(w, &P, b1, do2 ? b2 : b1, g_stop_after_ranges);
     counters[0] = w->ptadds; counters[1] = w->ptdups;
     mpz_get_str(x_hex, 16, P.X); mpz_get_str(z_hex, 16, P.Z);
     if (!check_factor(P.Z, w->nchk, f)) mpz_set_ui(f, 0);
@@ -783,14 +811,13 @@ uint32_t oracle_stage2_map(uint64_t b1, uint32_t *map, uint32_t cap)
  * 'I' [S]{3,4,5,9}* 'F'); returns the full length even if > cap. */
 uint64_t oracle_stage1_trace(uint64_t b1, uint8_t *ops, uint64_t cap)
 {
-    owork *w = work_new("fffffffb"); opt P; mpz_t A; uint64_t nump, *primes, len;
+    owork *w = work_new("fffffffb"); opt P; mpz_t A; uint64_t len;
     pt_init(&P); mpz_init(A);
     build_one_curve(w, P.X, P.Z, A, 11); mpz_set(w->s, A);
-    primes = sieve_range(0, b1 + 1000, &nump);
     g_trace = ops ? ops : (uint8_t *)&len; g_trace_cap = ops ? cap : 0; g_trace_len = 0;
-    ecm_stage1(w, &P, b1, primes, nump);
+    stage1_all_ranges(w, &P, b1, b1, 0);
     len = g_trace_len; g_trace = NULL;
-    free(primes); pt_clear(&P); mpz_clear(A); work_free(w);
+    pt_clear(&P); mpz_clear(A); work_free(w);
     return len;
 }
 

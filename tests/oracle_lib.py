@@ -24,6 +24,8 @@ def lib():
         L.oracle_ecm_curve.restype = ctypes.c_int
         L.oracle_ecm_curve_special.argtypes = [cp, cp, u64, u64, u64, cp, cp, cp, cp, cp, ctypes.POINTER(u32)]
         L.oracle_ecm_curve_special.restype = ctypes.c_int
+        L.oracle_set_prime_range.argtypes = [u64]
+        L.oracle_set_checkpoint.argtypes = [ctypes.c_int]
         L.oracle_build_curve.argtypes = [cp, u64, cp, cp]
         L.oracle_save_line.argtypes = [cp, u64, u64, cp, cp, cp, ctypes.c_size_t]
         L.oracle_pair.argtypes = [u64, u64, u32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), u32,
@@ -95,3 +97,13 @@ def stage1_trace(b1):
     buf = ctypes.create_string_buffer(n + 1)
     L.oracle_stage1_trace(b1, buf, n)
     return buf.raw[:n]
+
+
+def set_prime_range(r):
+    """Width of the prime ranges stage 1 is run in (0 = the reference's 1e8)."""
+    lib().oracle_set_prime_range(r)
+
+
+def set_checkpoint(ranges):
+    """Stop stage 1 after that many prime ranges (0 = run all): the state of checkpoint.txt."""
+    lib().oracle_set_checkpoint(ranges)

@@ -11,7 +11,7 @@ MAXBITS = 2048
 
 
 def usable(g):
-    return int(g["n"]).bit_length() <= MAXBITS
+    return int(g["n"]).bit_length() <= MAXBITS and g["b1"] <= 100000000      # B1 > 1e8: hours for 8 curves on one warp
 
 
 @pytest.mark.parametrize("name", sorted(k for k, g in GOLDEN.items() if usable(g)))
@@ -176,3 +176,68 @@ def test_tiny_b1_edge_cases(b1):
     for i in range(4):
         o = O.ecm_curve(N, b1, b1, 7 + i)
         assert (x[i], z[i]) == (o["x"], o["z"])
+
+
+def test_stage1_range_by_range_matches_oracle_checkpoints(monkeypatch):
+    """B1 beyond one prime range (1e8 in the reference; 3000 here through the test hooks): the reference calls
+    ecm_stage1 per range -- repeated doublings, first prime of later ranges skipped -- and saves the point after
+    each range to checkpoint.txt (ecm.c:1207-1311).  Range-by-range and one-go runs against the oracle."""
+    monkeypatch.setenv("ECM_B200_S1_RANGE", "3000")
+    O.set_prime_range(3000)
+    try:
+        N, b1 = composites()["syn415"], 10000
+        sig = [7, 1000003, 2 ** 63 + 11] + list(range(50, 53))
+        assert E.stage1_ranges(b1) == 4
+        ctx = E.EcmContext(N, len(sig))
+        try:
+            ctx.build_curves(sig)
+            with pytest.raises(E.EcmError):
+                ctx.stage1_range(b1, 1)                  # ranges must be taken in order
+            lasts = []
+            for r in range(4):
+                lasts.append(ctx.stage1_range(b1, r))
+                x, z, _ = ctx.read_stage1()
+                O.set_checkpoint(r + 1)
+                for i, s in enumerate(sig):
+                    o = O.ecm_curve(N, b1, b1, s)
+                    assert (x[i], z[i]) == (o["x"], o["z"]), (r, s)
+            assert lasts == [2999, 5987, 8999, 9973]
+            with pytest.raises(E.EcmError):
+                ctx.stage1(b1)                           # stage 1 is complete
+            O.set_checkpoint(0)
+            ctx.build_curves(sig)
+            ctx.stage1(b1)                               # the same in one call
+            assert ctx.read_stage1()[:2] == (x, z)
+            ctx.build_curves(sig)
+            ctx.stage1_range(b1, 0)
+            with pytest.raises(E.EcmError):
+                ctx.stage1(b1)                           # not after a range-by-range start
+        finally:
+            ctx.close()
+    finally:
+        O.set_prime_range(0)
+        O.set_checkpoint(0)
+
+
+def test_cli_writes_checkpoints(tmp_path, monkeypatch):
+    import os, subprocess
+    from conftest import ROOT
+    monkeypatch.setenv("ECM_B200_S1_RANGE", "2000")
+    O.set_prime_range(2000)
+    try:
+        N, b1, s0 = composites()["t35"], 5000, 424242
+        cli = os.path.join(ROOT, "avx-ecm_b200", "avx-ecm-b200")
+        subprocess.run([cli, str(N), "8", str(b1), "1", str(b1), str(s0)], cwd=tmp_path, capture_output=True, text=True, check=True)
+        ck = (tmp_path / "checkpoint.txt").read_text().splitlines(keepends=True)
+        assert len(ck) == 16                            # 3 ranges -> 2 checkpoints of 8 curves
+        for r, last in ((1, 1999), (2, 3989)):
+            O.set_checkpoint(r)
+            for i in range(8):
+                o = O.ecm_curve(N, b1, b1, s0 + i)
+                assert ck[(r - 1) * 8 + i] == E.save_line(s0 + i, last, N, o["x"], o["z"])
+        O.set_checkpoint(0)
+        save = (tmp_path / "save_b1.txt").read_text().splitlines(keepends=True)
+        assert save == [O.ecm_curve(N, b1, b1, s0 + i)["save_line"] for i in range(8)]
+    finally:
+        O.set_prime_range(0)
+        O.set_checkpoint(0)

@@ -19,7 +19,8 @@ def lanes_for(g):
     return list(range(n))
 
 
-@pytest.mark.parametrize("name", sorted(GOLDEN))
+# B1 > 1e8 takes minutes per curve on the CPU: tests/test_stage1_ranges_cpu.py (ECM_B200_SLOW=1) covers that vector
+@pytest.mark.parametrize("name", sorted(k for k, g in GOLDEN.items() if g["b1"] <= 100000000))
 def test_oracle_matches_reference(name):
     g = GOLDEN[name]
     N, b1, b2 = int(g["n"]), g["b1"], g["b2"]

@@ -80,6 +80,7 @@ def composites():
         "csh1m": 7908926676514675413083853032827063880118980193445471625562601469958414706043143581401715516956542424923236530406833110566233,
         "small96": 1000000007 * 998244353 * 4294967311,   # tiny composite: exercises factor/inversion-failure paths
         "csh150m": 19223719229397103735869895564468606263251785680561653388554202432164204897138631706690937388406707574740021324772129,
+        "syn206": synthetic(103, 103, 12348),     # 206 bits: the reference's smallest word count, for the B1 > 1e8 case
     }
 
 
@@ -104,6 +105,8 @@ def cases():
         ("small96_D30", c["small96"], 8, 50, 5000, 11),
         ("syn415_two_ranges", c["syn415"], 8, 2000, 100100000, 7),   # B2 spans two 1e8 prime ranges
         ("csh150m_b1_1e6_two_ranges", c["csh150m"], 8, 1000000, 150000000, 3018506502),   # test.csh line 6
+        # stage 1 over two 1e8 prime ranges (ecm.c:1207-1311): repeated doublings, skipped first prime, checkpoint.txt
+        ("syn206_b1_1.1e8_two_stage1_ranges", c["syn206"], 8, 110000000, 110000000, 1000003),
     ]
 
 
@@ -115,6 +118,8 @@ def run_case(name, N, curves, B1, B2, sigma0):
                              cwd=d, env=env, capture_output=True, text=True, check=True).stdout
         save = open(os.path.join(d, "save_b1.txt")).read().splitlines(keepends=True)
         taps = [l.split()[1:] for l in open(tap).read().splitlines()]
+        ckpt = os.path.join(d, "checkpoint.txt")
+        checkpoint = open(ckpt).read().splitlines(keepends=True) if os.path.exists(ckpt) else []
     maxbits = int(re.search(r"Choosing MAXBITS = (\d+)", out).group(1))
     Rinv = pow(1 << maxbits, -1, N)
     do2 = B2 > B1
@@ -122,6 +127,8 @@ def run_case(name, N, curves, B1, B2, sigma0):
     # gcd calls per batch: 8 x stage-1 Z, [inversion failures...], 8 x stage-2 acc (all with b == N)
     z1, acc, inv_fail_operands = [], [], []
     calls = [(int(a, 16), int(b, 16)) for a, b in taps if int(b, 16) == N]
+    if checkpoint:
+        calls = calls[len(checkpoint):]          # the checkpoint writer runs check_factor too (ecm.c:1262)
     per = []
     # split calls into batches: the reference processes batches sequentially
     idx = 0
@@ -142,8 +149,8 @@ def run_case(name, N, curves, B1, B2, sigma0):
     for m in re.finditer(r"found \S+ factor (\d+) in stage (\d) \(B\d = \d+\): thread 0, vec (\d+), sigma (\d+)", out):
         factors.append({"factor": m.group(1), "stage": int(m.group(2)), "lane": int(m.group(3)), "sigma": m.group(4)})
     cnt = {}
-    m = re.search(r"with (\d+) point-adds and (\d+) point-doubles", out)
-    cnt["s1_ptadds"], cnt["s1_ptdups"] = int(m.group(1)), int(m.group(2))
+    m = re.findall(r"with (\d+) point-adds and (\d+) point-doubles", out)[-1]     # the counters run on over the prime ranges
+    cnt["s1_ptadds"], cnt["s1_ptdups"] = int(m[0]), int(m[1])
     if do2:
         m = re.search(r"performed (\d+) pt-adds, (\d+) inversions, and (\d+) pair-muls", out)
         cnt["s2_ptadds"], cnt["s2_numinv"], cnt["s2_paired"] = map(int, m.groups())
@@ -155,7 +162,7 @@ def run_case(name, N, curves, B1, B2, sigma0):
         "maxbits_ref": maxbits, "save_lines": save,
         "z1_true_hex": [hex(x)[2:] for x in z1], "acc_true_hex": [hex(x)[2:] for x in acc],
         "inv_fail_gcd_calls": len(inv_fail_operands),
-        "factors": factors, "counts": cnt,
+        "factors": factors, "counts": cnt, "checkpoint_lines": checkpoint,
     }
 
 
