@@ -124,7 +124,7 @@ def test_error_behaviour_of_the_abi():
             ctx.build_curves(list(range(10, 10 + 65)))
         ctx.build_curves([7, 8, 9])
         with pytest.raises(E.EcmError, match="B1 out of range"):
-            ctx.stage1(200000000)
+            ctx.stage1(2000000001)          # beyond the 2e9 cap (ecm_b200.h)
         with pytest.raises(E.EcmError, match="not been run"):
             ctx.read_stage2()
         ctx.stage1(1000)
