@@ -124,9 +124,15 @@ ECM_SF_HD void special_fold_w(uint32_t (&r)[NL], const uint32_t (&T)[2 * NL], ui
     for (int j = 0; j < NL; j++) r[j] = (j <= W) ? x[j] : 0u;
 }
 
-// run-time W -> compile-time W.  LOW = lowest supported word index for this NL (bases shorter than that are
-// served by a smaller kernel set or by the generic Montgomery engine).
-template <int NL> struct SpecialRange { static constexpr int LOW = (NL > 10) ? NL - 9 : 2; };
+// run-time W -> compile-time W.  LOW = lowest supported word index for this NL: bases shorter than that are
+// served by the next smaller kernel set, so the build passes the previous compiled limb count as ECM_SP_LOW
+// (a base of more than 32*prev bits has k/32 >= prev); without it a window of 9 positions is compiled.
+#ifndef ECM_SP_LOW
+#define ECM_SP_LOW 0
+#endif
+template <int NL> struct SpecialRange {
+    static constexpr int LOW = (ECM_SP_LOW >= 2 && ECM_SP_LOW < NL) ? ECM_SP_LOW : ((NL > 10) ? NL - 9 : 2);
+};
 
 template <int NL, int W>
 ECM_SF_HD void special_fold_dispatch(uint32_t (&r)[NL], const uint32_t (&T)[2 * NL], uint32_t w, uint32_t s, int kind, uint32_t c)
