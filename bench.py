@@ -336,6 +336,36 @@ def main():
                                  "products_per_sec_adds_and_pairs": curves * (6 * cnt["s2_ptadds"] + cnt["s2_paired"]) * W / (s2_ms / 1e3),
                                  "table_read_GBs_algorithmic": table_bytes / (s2_ms / 1e3) / 1e9,
                                  "hbm_peak_GBs": 6540.8}
+        # special-form input (N | 2^415-1): the shift-and-fold kernels next to the Montgomery kernels on the same base
+        try:
+            sbase, sfb1 = (1 << 415) - 1, 30000
+            sf = {"base": "2^415-1", "b1": sfb1, "curves": curves}
+            ref_xz = None
+            for mode in ("fold", "montgomery"):
+                if mode == "montgomery":
+                    os.environ["ECM_B200_NO_FOLD"] = "1"
+                c3 = E.EcmContext(sbase, curves, device=local_rank, base=sbase)
+                try:
+                    best = None
+                    for _ in range(2):
+                        c3.build_curves(sig)
+                        c3.stage1(sfb1)
+                        ms3, _l = c3.last_timing()
+                        best = ms3 if best is None else min(best, ms3)
+                    xz = c3.read_stage1()[:2]
+                    sf[mode + "_curves_per_sec"] = curves / (best / 1e3)
+                    sf["uses_fold_" + mode] = c3.uses_fold
+                finally:
+                    c3.close()
+                if ref_xz is None:
+                    ref_xz = xz
+                sf["identical_residues"] = bool(xz == ref_xz)
+            sf["speedup"] = sf["fold_curves_per_sec"] / sf["montgomery_curves_per_sec"]
+            also["special_form_sample"] = sf
+        except Exception as e:          # a side measurement must never take the headline line down
+            also["special_form_sample"] = {"error": repr(e)}
+        finally:
+            os.environ.pop("ECM_B200_NO_FOLD", None)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
