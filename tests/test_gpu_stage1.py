@@ -241,3 +241,18 @@ def test_cli_writes_checkpoints(tmp_path, monkeypatch):
     finally:
         O.set_prime_range(0)
         O.set_checkpoint(0)
+
+
+def test_gpu_lines_are_valid_gmp_ecm_resume_points():
+    """Independent of the oracle: the (X:Z) the engine records must be [k]P0 on the Suyama curve of SIGMA
+    (plain Montgomery ladder on Python integers, tests/test_resume_lines_cpu.py) -- what `ecm -resume` continues."""
+    import random
+    from test_resume_lines_cpu import check_line
+    rng = random.Random(99)
+    for name, b1 in (("syn415", 20000), ("syn1024", 3000), ("t35", 50000)):
+        N = composites()[name]
+        r = E.vececm(N, 12, b1, b2=b1, sigma=rng.randrange(6, 2 ** 63))
+        assert [check_line(l, expect_n=N) for l in r["save_lines"]] == ["ok"] * 12
+    base = (1 << 277) - 1
+    r = E.vececm(base, 12, 5000, b2=5000, sigma=rng.randrange(6, 2 ** 63), base=base)
+    assert [check_line(l, expect_n=base, base=base) for l in r["save_lines"]] == ["ok"] * 12
