@@ -275,9 +275,9 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
         if (const char *e = getenv("ECM_B200_THREADS")) { uint32_t t = (uint32_t)atoi(e); if (t >= 32 && t <= S && t % 32 == 0) bestT = t; }
         c->T = bestT;
         c->groups_max = (max_curves + bestT - 1) / bestT;
-        c->G1 = Geom{bestT, S, NSLOT_S1};
+        c->G1 = Geom{bestT, (uint32_t)eng->stride_for_threads(bestT), NSLOT_S1};
     }
-    c->state_words = (size_t)c->groups_max * NSLOT_S1 * nl * eng->stride_s1;
+    c->state_words = (size_t)c->groups_max * NSLOT_S1 * nl * c->G1.stride;
     CUC(cudaMalloc(&c->d_state, c->state_words * 4));
     CUC(cudaMemsetAsync(c->d_state, 0, c->state_words * 4, c->stream));
     c->d_io_words = (size_t)4 * nl * max_curves + 64;

@@ -11,7 +11,9 @@ namespace ecmb200 {
 typedef std::vector<uint32_t> Big;
 
 struct Engine {
-    int nl = 0, stride_s1 = 0, smem_s1 = 0;      // stride_s1 = max threads per stage-1 block = lane stride of the state
+    int nl = 0, stride_s1 = 0, smem_s1 = 0;      // stride_s1 = max threads per stage-1 block
+    // lane stride of the stage-1 state for blocks of T threads (the stage-1 kernel instance serving T fixes it)
+    virtual int stride_for_threads(uint32_t T) const = 0;
     size_t params_bytes = 0;
     virtual ~Engine() {}
     virtual void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, uint32_t m0inv) = 0;

@@ -29,12 +29,18 @@ struct EngineT : Engine {
     {
         return ECM_SPECIAL && NL <= 32 && kbits >= 64 && (int)(kbits >> 5) >= SpecialRange<NL>::LOW && (int)(kbits >> 5) < NL;
     }
+    int stride_for_threads(uint32_t T) const override { return T <= (uint32_t)S1Small<NL>::MAXT ? S1Small<NL>::MAXT : S1Cfg<NL>::STRIDE; }
     const void *params_host() const override { return &P; }
     void set_params_device(const void *d) override { Pg = static_cast<const ModParams<NL> *>(d); }
     cudaError_t prepare() override
     {
-        cudaError_t e = cudaFuncSetAttribute(k_stage1<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s1);
+        cudaError_t e = cudaFuncSetAttribute(k_stage1<NL, S1Cfg<NL>::STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s1);
         if (e != cudaSuccess) return e;
+        if constexpr (S1Small<NL>::MAXT != S1Cfg<NL>::STRIDE) {
+            e = cudaFuncSetAttribute(k_stage1<NL, S1Small<NL>::MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     S1Cfg<NL>::per_thread * S1Small<NL>::MAXT);
+            if (e != cudaSuccess) return e;
+        }
         threads_pair = PairCfg<NL>::THREADS;
         use_pair_kernel = (NL <= 32);
         if (!use_pair_kernel) return cudaFuncSetAttribute(k_vm2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
@@ -74,7 +80,10 @@ struct EngineT : Engine {
     void stage1(cudaStream_t st, uint32_t blocks, uint32_t threads, uint32_t *state, const uint8_t *ops, uint64_t nops,
                 uint32_t chunk_len, uint32_t groups, uint64_t item0) override
     {
-        k_stage1<NL><<<blocks, threads, smem_s1, st>>>(P, state, ops, nops, chunk_len, groups, item0);
+        if (S1Small<NL>::MAXT != S1Cfg<NL>::STRIDE && threads <= (uint32_t)S1Small<NL>::MAXT)
+            k_stage1<NL, S1Small<NL>::MAXT><<<blocks, threads, S1Cfg<NL>::per_thread * S1Small<NL>::MAXT, st>>>(P, state, ops, nops, chunk_len, groups, item0);
+        else
+            k_stage1<NL, S1Cfg<NL>::STRIDE><<<blocks, threads, smem_s1, st>>>(P, state, ops, nops, chunk_len, groups, item0);
         count_launch();
     }
     void load_curves(cudaStream_t st, uint32_t *state, Geom G, uint32_t lanes, uint32_t count, const uint32_t *x, const uint32_t *s) override

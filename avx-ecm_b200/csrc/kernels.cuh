@@ -44,19 +44,27 @@ struct S1Cfg {
     static constexpr int nsmem = (NL > 32) ? NSMEM_S1 + 2 : NSMEM_S1;
     static constexpr int per_thread = nsmem * NL * 4;
     static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
-    // dual-product micro-ops (NL <= 16) want ~150 registers: at most 384 threads per block.  The fold kernels
-    // run their two products one after the other (~110 registers) and are latency-bound: 512 threads
-    static constexpr int cap = (NL <= 16) ? (ECM_SPECIAL ? (NL <= 10 ? 768 : NL <= 13 ? 640 : 512) : 384) : 768;
+    // the kernels are bound by dependent-issue latency, so the cap is what the register count of the unrolled
+    // dual product allows without spills (78 / 96 / 114 registers at 10 / 13 / 16 limbs); the host picks the
+    // block size per batch (ecm_gpu.cu)
+    static constexpr int cap = (NL <= 10) ? 768 : (NL <= 13) ? 640 : (NL <= 16) ? 512 : 768;
     static constexpr int STRIDE = fit > cap ? cap : fit;          // max threads per block = lane stride
     static constexpr int smem = per_thread * STRIDE;
 };
 
-template <int NL>
-__global__ void __launch_bounds__(S1Cfg<NL>::STRIDE, 1)
+// MAXT = the largest block this instance is launched with = lane stride of its state and shared-memory layout.
+// Two instances per limb count: blocks up to 384 threads keep the layout, shared-memory footprint and register
+// allocation the 65 536-curve configurations were tuned with; larger blocks (bigger batches, see the block-size
+// model in ecm_gpu.cu) use the wider one (measured at 13 limbs: a 640-lane layout costs the 384-thread
+// configuration 3 %, 7.64 -> 7.41 Tprod/s, while 640 threads on 94 720 curves reach 8.07).
+template <int NL> struct S1Small { static constexpr int MAXT = S1Cfg<NL>::STRIDE < 384 ? S1Cfg<NL>::STRIDE : 384; };
+
+template <int NL, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 k_stage1(const ModParams<NL> P, uint32_t *__restrict__ state, const uint8_t *__restrict__ ops,
          uint64_t nops, uint32_t chunk_len, uint32_t groups, uint64_t item0)
 {
-    constexpr int STRIDE = S1Cfg<NL>::STRIDE;
+    constexpr int STRIDE = MAXT;
     extern __shared__ uint32_t smem[];
     const uint64_t item = item0 + blockIdx.x;
     const uint32_t g = (uint32_t)(item % groups);
