@@ -385,8 +385,10 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches,
             "roofline": {"bound": "imad", "achieved": prod_rate / 1e9, "peak": peak_all / 1e9, "unit": "Gprod/s",
                          "frac": prod_rate / peak_all,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_final_stage1_ncu_full_summary.txt
-                         "traffic": 21007872,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (33.47 + 56.40 MB: the batch state is
+                         # re-read after the L2 flush between steps and dirty lines are written back),
+                         # profiles/r1_final_stage1_ncu_full_summary.txt; incidental for an IMAD-bound kernel
+                         "traffic": 89868544,
                          "note": "achieved = curves/s x 12974547 modmul/curve x (2n^2+n) products, n=%d; peak = fastest of three live probes on this GPU "
                                  "(IMAD.WIDE.U32.X chains with uniform / per-thread multiplier, register-resident 32-limb Montgomery loop) "
                                  "at %.0f MHz; the pipe's arithmetic ceiling is 32 products/clk/SM" % (nl, peak_clk)},
