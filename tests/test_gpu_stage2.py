@@ -124,3 +124,35 @@ def test_plain_c_client_runs_both_stages(tmp_path):
         o = O.ecm_curve(N, 20000, 2000000, 1000 + i)
         got = int(l.split("0x")[1], 16) if "factor 0x" in l else 0
         assert got == o["f2"], l
+
+
+def test_cli_on_two_gpus_writes_the_single_gpu_files(tmp_path, monkeypatch):
+    """The 4th argument (the reference's thread count) is the number of GPUs: one host thread and one context per
+    GPU, disjoint sigma slices, files merged in sigma order -- byte-identical to the one-GPU / reference output.
+    Also with stage-1 prime ranges (checkpoint.txt) and a special-form input.  Skipped on a one-GPU box."""
+    import os, subprocess
+    from conftest import ROOT
+    try:
+        ngpu = len(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.strip().splitlines())
+    except OSError:
+        ngpu = 0
+    if ngpu < 2:
+        pytest.skip("needs two GPUs")
+    cli = os.path.join(ROOT, "avx-ecm_b200", "avx-ecm-b200")
+    for name in ("syn415_b1_3e4_s1only", "small96_D210", "special_p523"):
+        g = GOLDEN[name]
+        d = tmp_path / name
+        d.mkdir()
+        subprocess.run([cli, g.get("expr", g["n"]), str(len(g["save_lines"])), str(g["b1"]), "2", str(g["b2"]), g["sigma0"]],
+                       cwd=d, capture_output=True, text=True, check=True)
+        assert open(d / "save_b1.txt").read() == "".join(g["save_lines"])
+    # range-by-range stage 1 on two GPUs == on one
+    monkeypatch.setenv("ECM_B200_S1_RANGE", "2000")
+    N = composites()["t35"]
+    outs = []
+    for gpus in ("1", "2"):
+        d = tmp_path / ("ranges" + gpus)
+        d.mkdir()
+        subprocess.run([cli, str(N), "10", "5000", gpus, "5000", "424242"], cwd=d, capture_output=True, text=True, check=True)
+        outs.append(((d / "checkpoint.txt").read_text(), (d / "save_b1.txt").read_text()))
+    assert outs[0] == outs[1] and outs[0][0].count("\n") == 20
