@@ -3,6 +3,7 @@
 // field operations (SURVEY facts 2, 3, 8 and Appendices A/B).
 #include "plan.hpp"
 #include <cstdlib>
+#include <thread>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -157,13 +158,26 @@ void plan_stage1(uint64_t b1, Stage1Plan &plan)
         }
         // the primes of this range below B1 without the first one, prac(p) repeated while p^k * p < B1 (ecm.c:1824-1832)
         std::vector<uint64_t> primes = primes_in_range(lo, std::min(b1, lo + kStage1Range));
+        // the multiplier search (ten trial chains per prime, ecm.c:574-584) is nine tenths of the planning time and
+        // independent per prime: do it on all host threads, then emit sequentially
+        std::vector<uint8_t> mult(primes.size(), 0);
+        {
+            const size_t np = primes.size();
+            unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+            if (np < 20000) nt = 1;
+            auto work = [&](size_t a, size_t b) { for (size_t i = std::max<size_t>(a, 1); i < b; i++) mult[i] = (uint8_t)best_multiplier(primes[i]); };   // primes[0] is never used
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nt; t++) th.emplace_back(work, np * t / nt, np * (t + 1) / nt);
+            work(0, np / nt);
+            for (auto &x : th) x.join();
+        }
         uint64_t last = 0;
         for (size_t i = 1; i < primes.size(); i++) {
             const uint64_t p = primes[i];
             last = p;
             uint64_t c = 1;
             do {
-                const double v = kPracV[best_multiplier(p)];
+                const double v = kPracV[mult[i]];
                 em.make_role(LB, em.pslot);           // B = P (no copy), C = copy, A = 2P
                 em.put(M_INIT);
                 plan.ptdups++;
