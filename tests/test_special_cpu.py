@@ -72,3 +72,28 @@ def test_create_special_rejects_bad_arguments():
     even = (ctypes.c_uint32 * 2)(8, 1)
     assert L.ecm_b200_create_special(ctypes.byref(h), 0, n, 2, even, 2, 8) == -1
     assert L.ecm_b200_create_special(ctypes.byref(h), 0, n, 2, None, 0, 8) == -1
+
+
+# ---- classification only: more shapes, as decided by the compiled reference (tools/gen_classify_golden.py) ------
+import json
+CLASSIFY = json.load(open(os.path.join(ROOT, "tests", "golden_classify.json")))
+
+
+@pytest.mark.parametrize("rec", CLASSIFY, ids=[r["expr"][:40] for r in CLASSIFY])
+def test_classification_of_more_shapes_matches_reference(rec):
+    N = evaluate(rec["expr"])
+    if rec["error"]:                                   # the reference gives up: more than three distinct odd primes in k
+        with pytest.raises(ValueError):
+            E.special_form(N)
+        r = subprocess.run([CLI, "--classify", rec["expr"]], capture_output=True, text=True)
+        assert r.returncode == 1 and "too many distinct odd factors" in r.stdout
+        return
+    f = E.special_form(N)
+    assert f["n"] == int(rec["n"]) and f["kind"] == rec["kind"]
+    out = subprocess.run([CLI, "--classify", rec["expr"]], capture_output=True, text=True, check=True).stdout
+    m = re.search(r"kind (-?\d+) k (\d+) n (\d+) base (\d+)", out)
+    assert int(m.group(1)) == rec["kind"] and int(m.group(3)) == int(rec["n"])
+    assert ("determined to be faster by REDC" in out) == rec["redc_forced"]
+    if rec["kind"]:
+        assert f["k"] == rec["k"] == int(m.group(2))
+        assert int(m.group(4)) == f["base"]
