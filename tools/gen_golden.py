@@ -180,6 +180,8 @@ def special_cases():
         ("special_pm220_57", "2^220-57", 8, 3000, 300000, 424242421),
         ("special_m127x", "(2^254-1)/(2^127-1)/3", 8, 1000, 100000, 77777771),   # 2^127+1 over 3: found as 2^127+1
         ("special_redc", "36667531*129175771*58052548129*83207209", 8, 2000, 200000, 1000003),  # | 2^523+1, REDC wins
+        ("special_pm128_169", "2^64+13", 8, 1500, 150000, 31415927),            # found as 2^128-169: N far shorter than its base
+        ("special_p128", "(2^128+1)/59649589127497217", 8, 1500, 150000, 27182819),  # k a multiple of 32
     ]
 
 
