@@ -68,6 +68,7 @@ def test_oracle_checkpoints_are_prefixes(prime_range):
 
 
 @SLOW
+@pytest.mark.timeout(3600)
 def test_plan_matches_oracle_trace_beyond_1e8():
     b1 = 110000000
     ops, adds, dups = E.plan_stage1(b1)
@@ -79,6 +80,7 @@ def test_plan_matches_oracle_trace_beyond_1e8():
 
 
 @SLOW
+@pytest.mark.timeout(7200)
 def test_oracle_matches_reference_beyond_1e8():
     g = GOLDEN["syn206_b1_1.1e8_two_stage1_ranges"]
     N, b1, s0 = int(g["n"]), g["b1"], int(g["sigma0"])
