@@ -64,11 +64,14 @@ def lib():
         "ecm_b200_timer": (c.c_int, [vp, c.c_int, c.POINTER(c.c_float)]),
         "ecm_b200_read_stage1": (c.c_int, [vp, u32p, u32p, u8p, u32p]),
         "ecm_b200_stage2": (c.c_int, [vp, c.c_uint64, c.c_uint64]),
+        "ecm_b200_stage2_init": (c.c_int, [vp, c.c_uint64, c.POINTER(c.c_int)]),
+        "ecm_b200_stage2_range": (c.c_int, [vp, c.c_uint32, u32p, u32p, c.c_uint32]),
         "ecm_b200_read_stage2": (c.c_int, [vp, u32p, u8p, u32p, u8p]),
         "ecm_b200_stage2_counters": (c.c_int, [vp, u64p, u64p, u64p, u64p]),
         "ecm_b200_plan_stage1": (c.c_uint64, [c.c_uint64, u8p, c.c_uint64, u64p]),
         "ecm_b200_plan_stage2": (c.c_uint64, [c.c_uint64, c.c_uint64, u64p]),
         "ecm_b200_stage2_program": (c.c_uint64, [c.c_uint64, c.c_uint64, c.c_int, u64p, c.c_uint64, u32p]),
+        "ecm_b200_stage2_pairmap_program": (c.c_uint64, [c.c_uint64, c.c_uint32, u32p, u32p, c.c_uint32, u64p, c.c_uint64]),
         "ecm_b200_pair": (c.c_uint32, [c.c_uint64, c.c_uint64, c.c_uint32, c.c_uint32, u32p, u32p, c.c_uint32, u32p, u32p]),
         "ecm_b200_stage2_params": (None, [c.c_uint64, u32p, u32p, u32p, u32p]),
         "ecm_b200_fieldop": (c.c_int, [vp, c.c_int, c.c_uint32, u32p, u32p, u32p, c.c_int]),
@@ -86,7 +89,8 @@ def lib():
 EXPORTS = ["ecm_b200_create", "ecm_b200_create_special", "ecm_b200_uses_fold", "ecm_b200_destroy", "ecm_b200_last_error", "ecm_b200_limbs", "ecm_b200_build_curves",
            "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_ranges", "ecm_b200_stage1_range", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
            "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_stage1_progress", "ecm_b200_flush_l2", "ecm_b200_timer", "ecm_b200_read_stage1", "ecm_b200_stage2",
-           "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_stage2_program", "ecm_b200_pair", "ecm_b200_stage2_params",
+           "ecm_b200_stage2_init", "ecm_b200_stage2_range",
+           "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_stage2_program", "ecm_b200_stage2_pairmap_program", "ecm_b200_pair", "ecm_b200_stage2_params",
            "ecm_b200_fieldop", "ecm_b200_launch_count", "ecm_b200_last_timing", "ecm_b200_measure_imad_peak"]
 
 
@@ -230,6 +234,19 @@ class EcmContext:
     def stage2(self, b1, b2):
         _check(lib().ecm_b200_stage2(self._h, b1, b2))
 
+    def stage2_init(self, b1):
+        """ecm_stage2_init (ecm.c:2201-2340) for the whole batch; -> foundDuringInv"""
+        f = ctypes.c_int()
+        _check(lib().ecm_b200_stage2_init(self._h, b1, ctypes.byref(f)))
+        return bool(f.value)
+
+    def stage2_range(self, amin, pm_v, pm_u):
+        """ecm_stage2_pair (ecm.c:2342-2540) on a caller-supplied pairmap starting at window index amin"""
+        n = len(pm_v)
+        v = (ctypes.c_uint32 * max(1, n))(*pm_v)
+        u = (ctypes.c_uint32 * max(1, n))(*pm_u)
+        _check(lib().ecm_b200_stage2_range(self._h, amin, v, u, n))
+
     def read_stage2(self):
         n, nl = self.count, self.nl
         acc = (ctypes.c_uint32 * (nl * n))()
@@ -298,6 +315,18 @@ def stage2_program(b1, b2, which):
     L.ecm_b200_stage2_program(b1, b2, which, buf, n, lay)
     names = ("npb", "pbx", "pbz", "pba", "pax", "paz", "pai", "paa", "qx", "qz", "pdx", "pdz", "entries")
     return list(buf[:n]), dict(zip(names, lay))
+
+
+def stage2_pairmap_program(b1, amin, pm_v, pm_u):
+    """-> instruction words of the program ecm_b200_stage2_range runs for a caller pairmap; [] when it is rejected."""
+    L = lib()
+    n = len(pm_v)
+    v = (ctypes.c_uint32 * max(1, n))(*pm_v)
+    u = (ctypes.c_uint32 * max(1, n))(*pm_u)
+    k = L.ecm_b200_stage2_pairmap_program(b1, amin, v, u, n, None, 0)
+    buf = (ctypes.c_uint64 * max(1, k))()
+    L.ecm_b200_stage2_pairmap_program(b1, amin, v, u, n, buf, k)
+    return list(buf[:k])
 
 
 def pair(lo, hi, D, U=16):

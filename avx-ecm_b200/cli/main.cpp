@@ -12,6 +12,8 @@
 #include <string.h>
 #include <sys/time.h>
 #include <unistd.h>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -27,59 +29,6 @@ static double now()
 
 // Knuth's MMIX LCG, the generator the reference draws random sigmas from (main.c:993-998)
 static uint64_t lcg_next(uint64_t *s) { *s = 6364136223846793005ULL * *s + 1442695040888963407ULL; return *s; }
-
-struct Shard {
-    int gpu = 0;
-    uint32_t first = 0, count = 0;
-    std::vector<uint64_t> sigma;
-    std::vector<uint32_t> X, Z, G1, G2;
-    std::vector<uint8_t> f1, f2;
-    // state after every stage-1 prime range but the last (what the reference appends to checkpoint.txt)
-    struct Checkpoint { uint64_t last_prime; std::vector<uint32_t> X, Z, G; std::vector<uint8_t> f; };
-    std::vector<Checkpoint> ckpt;
-    int limbs = 0;
-    double t_build = 0, t_s1 = 0, t_s2 = 0;
-    std::string error;
-};
-
-// base32 empty: generic input.  Otherwise the curve arithmetic runs modulo the base number 2^k-c / 2^k+1 and
-// only the factor checks use N (main.c:597-616, ecm.c:1108-1119).
-static void run_shard(Shard *s, const std::vector<uint32_t> *n32, const std::vector<uint32_t> *base32, uint64_t b1, uint64_t b2, bool do2)
-{
-    ecm_b200_ctx *ctx = NULL;
-    const int rc0 = base32->empty() ? ecm_b200_create(&ctx, s->gpu, n32->data(), (int)n32->size(), s->count)
-                                    : ecm_b200_create_special(&ctx, s->gpu, base32->data(), (int)base32->size(), n32->data(),
-                                                              (int)n32->size(), s->count);
-    if (rc0) { s->error = ecm_b200_last_error(); return; }
-    const int L = s->limbs = ecm_b200_limbs(ctx);
-    const size_t words = (size_t)L * s->count;
-    s->X.resize(words); s->Z.resize(words); s->G1.resize(words); s->f1.resize(s->count);
-    double t0 = now();
-    int rc = ecm_b200_build_curves(ctx, s->count, s->sigma.data());
-    s->t_build = now() - t0; t0 = now();
-    uint32_t nranges = 1;
-    if (!rc) rc = ecm_b200_stage1_ranges(b1, &nranges);
-    if (!rc && nranges <= 1) rc = ecm_b200_stage1(ctx, b1);
-    for (uint32_t r = 0; !rc && nranges > 1 && r < nranges; r++) {           // vececm's range loop, ecm.c:1207-1311
-        uint64_t last = 0;
-        rc = ecm_b200_stage1_range(ctx, b1, r, &last);
-        if (rc || r + 1 == nranges) break;
-        Shard::Checkpoint c;
-        c.last_prime = last; c.X.resize(words); c.Z.resize(words); c.G.resize(words); c.f.resize(s->count);
-        rc = ecm_b200_read_stage1(ctx, c.X.data(), c.Z.data(), c.f.data(), c.G.data());
-        s->ckpt.push_back(std::move(c));
-    }
-    if (!rc) rc = ecm_b200_read_stage1(ctx, s->X.data(), s->Z.data(), s->f1.data(), s->G1.data());
-    s->t_s1 = now() - t0; t0 = now();
-    if (!rc && do2) {
-        s->G2.resize(words); s->f2.resize(s->count);
-        rc = ecm_b200_stage2(ctx, b1, b2);
-        if (!rc) rc = ecm_b200_read_stage2(ctx, NULL, s->f2.data(), s->G2.data(), NULL);
-        s->t_s2 = now() - t0;
-    }
-    if (rc) s->error = ecm_b200_last_error();
-    ecm_b200_destroy(ctx);
-}
 
 static void limbs_to_mpz(mpz_t out, const std::vector<uint32_t> &buf, int L, uint32_t count, uint32_t i)
 {
@@ -98,6 +47,114 @@ static void report(FILE *res, mpz_t f, int stage, uint64_t bound, uint32_t curve
         gmp_fprintf(res, "\nfound %s factor %Zd in stage %d (B%d = %" PRIu64 "): curve %d, thread %d, vec %d, sigma %" PRIu64 "\n",
                     ftype, f, stage, stage, bound, (int)curve, 0, (int)(curve % 8), sigma);
     fflush(stdout);
+}
+
+// Output files are appended to as soon as the data exists, like the reference does: checkpoint.txt after every
+// stage-1 prime range but the last (ecm.c:1237-1311), save_b1.txt right after stage 1 and BEFORE stage 2 starts
+// (ecm.c:1319-1388), so that a failure later on (stage 2 running out of memory on one GPU, a crash hours into a large
+// B1) never costs finished stage-1 work.  The GPUs finish at different times; a ticket per file section keeps the
+// lines in sigma order (= the reference's batch/thread/lane order with threads=1): shard g writes section k only
+// after shards 0..g-1 have, and a shard that failed passes its turn without writing.
+struct Output {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> turn;                 // per section: the shard whose turn it is
+    mpz_t N;
+    FILE *res = nullptr;                   // ecm_results.txt
+    int found = 0;
+    template <class F> void in_turn(size_t section, int shard, F &&write)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return turn[section] == shard; });
+        write();
+        turn[section]++;
+        cv.notify_all();
+    }
+};
+
+struct Shard {
+    int gpu = 0;
+    uint32_t first = 0, count = 0;
+    std::vector<uint64_t> sigma;
+    int limbs = 0;
+    double t_build = 0, t_s1 = 0, t_s2 = 0;
+    std::string error;
+};
+
+// one section of resume lines for this shard: checkpoint.txt (B1 = last prime used) or save_b1.txt
+static void write_lines(Output *out, const Shard *s, const char *file, uint64_t b1_printed, bool announce,
+                        const std::vector<uint32_t> &X, const std::vector<uint32_t> &Z, const std::vector<uint8_t> &fl,
+                        const std::vector<uint32_t> &G)
+{
+    FILE *fp = fopen(file, "a");
+    if (!fp) printf("could not open %s for appending, Stage 1 data will not be saved\n", file);
+    if (announce && s->gpu == 0) printf("Saving checkpoint after p=%" PRIu64 "\n", b1_printed);
+    mpz_t x, z, f; mpz_init(x); mpz_init(z); mpz_init(f);
+    for (uint32_t i = 0; i < s->count; i++) {
+        limbs_to_mpz(x, X, s->limbs, s->count, i);
+        limbs_to_mpz(z, Z, s->limbs, s->count, i);
+        if (!announce && mpz_sgn(z) == 0) printf("something failed: curve %u has zero result\n", s->first + i);
+        if (fl[i]) { limbs_to_mpz(f, G, s->limbs, s->count, i); report(out->res, f, 1, b1_printed, s->first + i, s->sigma[i]); out->found = 1; }
+        if (fp) {
+            fprintf(fp, "METHOD=ECM; SIGMA=%" PRIu64 "; B1=%" PRIu64 "; ", s->sigma[i], b1_printed);
+            gmp_fprintf(fp, "N=0x%Zx; X=0x%Zx; Z=0x%Zx; PROGRAM=AVX-ECM;\n", out->N, x, z);
+        }
+    }
+    mpz_clear(x); mpz_clear(z); mpz_clear(f);
+    if (fp) fclose(fp);
+    if (out->res) fflush(out->res);
+}
+
+// base32 empty: generic input.  Otherwise the curve arithmetic runs modulo the base number 2^k-c / 2^k+1 and
+// only the factor checks use N (main.c:597-616, ecm.c:1108-1119).
+static void run_shard(Shard *s, Output *out, const std::vector<uint32_t> *n32, const std::vector<uint32_t> *base32, uint64_t b1,
+                      uint64_t b2, bool do2, uint32_t nranges)
+{
+    size_t section = 0;                                   // next file section this shard owes a turn for
+    const size_t nsections = (size_t)nranges + (do2 ? 1 : 0);   // checkpoints, save_b1, stage-2 reports
+    auto give_up = [&](const char *msg) {
+        s->error = msg;
+        for (; section < nsections; section++) out->in_turn(section, s->gpu, [] {});
+    };
+    ecm_b200_ctx *ctx = NULL;
+    const int rc0 = base32->empty() ? ecm_b200_create(&ctx, s->gpu, n32->data(), (int)n32->size(), s->count)
+                                    : ecm_b200_create_special(&ctx, s->gpu, base32->data(), (int)base32->size(), n32->data(),
+                                                              (int)n32->size(), s->count);
+    if (rc0) { give_up(ecm_b200_last_error()); return; }
+    const int L = s->limbs = ecm_b200_limbs(ctx);
+    const size_t words = (size_t)L * s->count;
+    std::vector<uint32_t> X(words), Z(words), G(words);
+    std::vector<uint8_t> fl(s->count);
+    double t0 = now();
+    int rc = ecm_b200_build_curves(ctx, s->count, s->sigma.data());
+    s->t_build = now() - t0; t0 = now();
+    if (!rc && nranges <= 1) rc = ecm_b200_stage1(ctx, b1);
+    for (uint32_t r = 0; !rc && nranges > 1 && r < nranges; r++) {           // vececm's range loop, ecm.c:1207-1311
+        uint64_t last = 0;
+        rc = ecm_b200_stage1_range(ctx, b1, r, &last);
+        if (rc || r + 1 == nranges) break;
+        rc = ecm_b200_read_stage1(ctx, X.data(), Z.data(), fl.data(), G.data());
+        if (rc) break;
+        out->in_turn(section++, s->gpu, [&] { write_lines(out, s, "checkpoint.txt", last, true, X, Z, fl, G); });
+    }
+    if (!rc) rc = ecm_b200_read_stage1(ctx, X.data(), Z.data(), fl.data(), G.data());
+    s->t_s1 = now() - t0; t0 = now();
+    if (rc) { give_up(ecm_b200_last_error()); ecm_b200_destroy(ctx); return; }
+    out->in_turn(section++, s->gpu, [&] { write_lines(out, s, "save_b1.txt", b1, false, X, Z, fl, G); });
+    if (do2) {
+        rc = ecm_b200_stage2(ctx, b1, b2);
+        if (!rc) rc = ecm_b200_read_stage2(ctx, NULL, fl.data(), G.data(), NULL);
+        s->t_s2 = now() - t0;
+        if (rc) { give_up(ecm_b200_last_error()); ecm_b200_destroy(ctx); return; }
+        out->in_turn(section++, s->gpu, [&] {
+            mpz_t f; mpz_init(f);
+            for (uint32_t i = 0; i < s->count; i++)
+                if (fl[i]) { limbs_to_mpz(f, G, s->limbs, s->count, i); report(out->res, f, 2, b2, s->first + i, s->sigma[i]); out->found = 1; }
+            mpz_clear(f);
+            if (out->res) fflush(out->res);
+        });
+    }
+    ecm_b200_destroy(ctx);
 }
 
 int main(int argc, char **argv)
@@ -123,8 +180,8 @@ int main(int argc, char **argv)
     }
     const double t_start = now();
     printf("starting process %d\n", (int)getpid());
-    mpz_t N, x, z, f;
-    mpz_init(N); mpz_init(x); mpz_init(z); mpz_init(f);
+    mpz_t N;
+    mpz_init(N);
     std::string err = calc_eval(argv[1], N);
     if (!err.empty()) { printf("could not evaluate input expression: %s\n", err.c_str()); return 1; }
     if (mpz_cmp_ui(N, 3) < 0 || !mpz_odd_p(N)) { printf("input must be an odd integer > 2\n"); return 1; }
@@ -173,60 +230,25 @@ int main(int argc, char **argv)
         }
     }
     printf("\nCommencing curves 0-%u of %u\n", numcurves - 1, numcurves);
+    uint32_t nranges = 1;
+    if (ecm_b200_stage1_ranges(b1, &nranges) || nranges < 1) nranges = 1;
+    Output out;
+    mpz_init(out.N); mpz_set(out.N, N);
+    out.res = fopen("ecm_results.txt", "a");
+    out.turn.assign((size_t)nranges + (do2 ? 1 : 0), 0);
     std::vector<std::thread> th;
-    for (int g = 0; g < gpus; g++) th.emplace_back(run_shard, &shards[g], &n32, &base32, b1, b2, do2);
+    for (int g = 0; g < gpus; g++) th.emplace_back(run_shard, &shards[g], &out, &n32, &base32, b1, b2, do2, nranges);
     for (auto &t : th) t.join();
+    if (out.res) fclose(out.res);
     double ts1 = 0, ts2 = 0, tb = 0;
+    int failed = 0;
     for (auto &s : shards) {
-        if (!s.error.empty()) { printf("GPU %d: %s\n", s.gpu, s.error.c_str()); return 1; }
+        if (!s.error.empty()) { printf("GPU %d: %s\n", s.gpu, s.error.c_str()); failed = 1; }
         ts1 = std::max(ts1, s.t_s1); ts2 = std::max(ts2, s.t_s2); tb = std::max(tb, s.t_build);
     }
     printf("Building curves took %1.4f seconds.\n", tb);
     printf("Stage 1 took %1.4f seconds\n", ts1);
-
-    int found = 0;
-    FILE *res = fopen("ecm_results.txt", "a");
-    // checkpoint.txt: one block of lines per finished prime range, B1 = the last prime used (ecm.c:1237-1311)
-    for (size_t r = 0; r < shards[0].ckpt.size(); r++) {
-        FILE *ck = fopen("checkpoint.txt", "a");
-        if (!ck) { printf("could not open checkpoint.txt for appending, Stage 1 data will not be saved\n"); break; }
-        printf("Saving checkpoint after p=%" PRIu64 "\n", shards[0].ckpt[r].last_prime);
-        for (auto &s : shards) {
-            const Shard::Checkpoint &c = s.ckpt[r];
-            for (uint32_t i = 0; i < s.count; i++) {
-                limbs_to_mpz(x, c.X, s.limbs, s.count, i);
-                limbs_to_mpz(z, c.Z, s.limbs, s.count, i);
-                if (c.f[i]) { limbs_to_mpz(f, c.G, s.limbs, s.count, i); report(res, f, 1, c.last_prime, s.first + i, s.sigma[i]); found = 1; }
-                fprintf(ck, "METHOD=ECM; SIGMA=%" PRIu64 "; B1=%" PRIu64 "; ", s.sigma[i], c.last_prime);
-                gmp_fprintf(ck, "N=0x%Zx; X=0x%Zx; Z=0x%Zx; PROGRAM=AVX-ECM;\n", N, x, z);
-            }
-        }
-        fclose(ck);
-    }
-    // save_b1.txt, in sigma order = batch/thread/lane order of the reference with threads=1
-    FILE *save = fopen("save_b1.txt", "a");
-    if (!save) printf("could not open save_b1.txt for appending, Stage 1 data will not be saved\n");
-    for (auto &s : shards) {
-        for (uint32_t i = 0; i < s.count; i++) {
-            limbs_to_mpz(x, s.X, s.limbs, s.count, i);
-            limbs_to_mpz(z, s.Z, s.limbs, s.count, i);
-            if (mpz_sgn(z) == 0) printf("something failed: curve %u has zero result\n", s.first + i);
-            if (s.f1[i]) { limbs_to_mpz(f, s.G1, s.limbs, s.count, i); report(res, f, 1, b1, s.first + i, s.sigma[i]); found = 1; }
-            if (save) {
-                fprintf(save, "METHOD=ECM; SIGMA=%" PRIu64 "; B1=%" PRIu64 "; ", s.sigma[i], b1);
-                gmp_fprintf(save, "N=0x%Zx; X=0x%Zx; Z=0x%Zx; PROGRAM=AVX-ECM;\n", N, x, z);
-            }
-        }
-    }
-    if (save) fclose(save);
-    if (do2) {
-        printf("Stage 2 took %1.4f seconds\n", ts2);
-        for (auto &s : shards)
-            for (uint32_t i = 0; i < s.count; i++)
-                if (s.f2[i]) { limbs_to_mpz(f, s.G2, s.limbs, s.count, i); report(res, f, 2, b2, s.first + i, s.sigma[i]); found = 1; }
-    }
-    if (res) fclose(res);
+    if (do2) printf("Stage 2 took %1.4f seconds\n", ts2);
     printf("Process took %1.4f seconds.\n", now() - t_start);
-    (void)found;
-    return 0;
+    return failed;
 }

@@ -8,7 +8,8 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <thread>
-#include <chrono>
+#include <mutex>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -159,6 +160,11 @@ struct ecm_b200_ctx {
     uint32_t *d_acc = nullptr; uint8_t *d_fail = nullptr;       // per batch curve: accumulator (Montgomery form), inversion-failure flag
     bool stage2_done = false;
     float s2_ms = 0; uint32_t s2_launches = 0; uint32_t s2_waves = 0;
+    // stage-2 wave buffers, kept across calls (s2_reserve)
+    uint32_t *d_tab = nullptr, *d_state2 = nullptr; uint8_t *d_wfail = nullptr; uint64_t *d_code = nullptr;
+    size_t s2_tab_bytes = 0, s2_state_bytes = 0, s2_code_bytes = 0; uint32_t s2_fail_cap = 0;
+    uint32_t s2_cap = 0, s2_first = 0, s2_n = 0, s2_groups = 0;      // current wave
+    bool s2_open = false;       // ecm_b200_stage2_init done: tables resident, ecm_b200_stage2_range may follow
 };
 
 extern "C" {
@@ -300,6 +306,7 @@ void ecm_b200_destroy(ecm_b200_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_state); cudaFree(c->d_ops); cudaFree(c->d_io); cudaFree(c->d_flags); cudaFree(c->d_params); cudaFree(c->d_chk); cudaFree(c->d_flush); cudaFree(c->d_acc); cudaFree(c->d_fail);
+    cudaFree(c->d_tab); cudaFree(c->d_state2); cudaFree(c->d_wfail); cudaFree(c->d_code);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -317,6 +324,7 @@ static int set_count(ecm_b200_ctx *c, uint32_t count)
     c->groups = (count + c->T - 1) / c->T;
     c->have_curves = true; c->stage1_done = false; c->p_slot = 0; c->next_range = 0; c->seg_done = false;
     c->total_items = c->next_item = 0; c->launches_total = c->launches_issued = 0;
+    c->s2_open = false; c->stage2_done = false;
     return ECM_B200_OK;
 }
 
@@ -357,6 +365,11 @@ int ecm_b200_build_curves(ecm_b200_ctx *c, uint32_t count, const uint64_t *sigma
     return ECM_B200_OK;
 }
 
+static bool s1_in_progress(const ecm_b200_ctx *c)
+{
+    return (c->total_items != 0 && !c->seg_done) || (c->next_range != 0 && !c->stage1_done);
+}
+
 // plan for b1 on the device; the schedule of one segment [begin, end) of its op stream
 static int stage1_prepare(ecm_b200_ctx *c, uint64_t b1)
 {
@@ -377,6 +390,8 @@ static int stage1_prepare(ecm_b200_ctx *c, uint64_t b1)
         c->plan_on_device = true;
     }
     if (c->stage1_done) return fail(ECM_B200_ESTATE, "stage 1 already run on this batch");
+    if (c->total_items != 0 && !c->seg_done)
+        return fail(ECM_B200_ESTATE, "a stage-1 segment is still in progress on this batch (finish it with ecm_b200_stage1_step, or build the curves again)");
     return ECM_B200_OK;
 }
 
@@ -623,10 +638,100 @@ static int run_program(ecm_b200_ctx *c, const std::vector<uint64_t> &host_code, 
     return run_vm2(c, d_code + seg, n - seg, state2, cap2, tab, groups, inv_fail);
 }
 
-int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
+// ---- stage-2 device buffers: tables, slot file, failure flags and program buffer of one wave.  Allocated on first
+// use and kept by the context (a 65 536-curve wave at 415 bits is ~80 GB: allocating it per call cost more than the
+// set-up program); re-allocated only when a later call needs more.
+static int s2_reserve(ecm_b200_ctx *c, uint32_t entries, uint32_t cap2, size_t code_bytes)
+{
+    const int nl = c->nl;
+    const size_t tab_b = (size_t)entries * nl * 4 * cap2, st_b = (size_t)c->eng->nslot_s2 * nl * 4 * cap2;
+    if (tab_b > c->s2_tab_bytes) {
+        cudaFree(c->d_tab); c->d_tab = nullptr; c->s2_tab_bytes = 0;
+        CU(cudaMalloc(&c->d_tab, tab_b)); c->s2_tab_bytes = tab_b;
+    }
+    if (st_b > c->s2_state_bytes) {
+        cudaFree(c->d_state2); c->d_state2 = nullptr; c->s2_state_bytes = 0;
+        CU(cudaMalloc(&c->d_state2, st_b)); c->s2_state_bytes = st_b;
+    }
+    if (cap2 > c->s2_fail_cap) {
+        cudaFree(c->d_wfail); c->d_wfail = nullptr; c->s2_fail_cap = 0;
+        CU(cudaMalloc(&c->d_wfail, cap2)); c->s2_fail_cap = cap2;
+    }
+    if (code_bytes > c->s2_code_bytes) {
+        cudaFree(c->d_code); c->d_code = nullptr; c->s2_code_bytes = 0;
+        CU(cudaMalloc(&c->d_code, code_bytes + 64)); c->s2_code_bytes = code_bytes;
+    }
+    if (!c->d_acc) { CU(cudaMalloc(&c->d_acc, (size_t)nl * 4 * c->max_curves)); CU(cudaMalloc(&c->d_fail, c->max_curves)); }
+    return ECM_B200_OK;
+}
+
+// curves per wave that the device memory allows (tables + slot file per curve), a multiple of the group size
+static int s2_wave_capacity(ecm_b200_ctx *c, uint32_t entries, size_t code_bytes, uint32_t *cap_out)
+{
+    const uint32_t T = c->eng->threads_s2;
+    const size_t per_curve = ((size_t)entries + c->eng->nslot_s2) * c->nl * 4 + 1;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    free_b += c->s2_tab_bytes + c->s2_state_bytes + c->s2_fail_cap + c->s2_code_bytes;    // ours to re-use
+    const size_t budget = (size_t)((double)free_b * 0.90) - std::min<size_t>(code_bytes + (64u << 20), free_b / 4);
+    uint32_t cap2 = (uint32_t)std::min<size_t>((c->count + T - 1) / T * T, budget / per_curve / T * T);
+    if (cap2 < T) return fail(ECM_B200_ENOMEM, "not enough device memory for one stage-2 group");
+    if (const char *e = getenv("ECM_B200_S2_WAVE")) {        // test hook: force small waves
+        const uint32_t w = ((uint32_t)atoi(e) + T - 1) / T * T;
+        if (w >= T && w < cap2) cap2 = w;
+    }
+    *cap_out = cap2;
+    return ECM_B200_OK;
+}
+
+// stage 2 starts from the point stage 1 left (or from freshly loaded curves: resuming save_b1.txt lines), never from
+// the middle of a stage-1 run
+static int s2_check_start(ecm_b200_ctx *c, uint64_t b1)
 {
     if (!c) return fail(ECM_B200_EINVAL, "null context");
     if (!c->have_curves) return fail(ECM_B200_ESTATE, "no curves loaded");
+    if (s1_in_progress(c)) return fail(ECM_B200_ESTATE, "stage 1 is still in progress on this batch");
+    const Stage2Params prm = stage2_params(b1);
+    if (b1 < 2 || (b1 + prm.D) / (2 * (uint64_t)prm.D) == 0)
+        return fail(ECM_B200_EINVAL, "B1 too small for stage 2: the first giant step [A-w]Q would be negative (B1 >= 30 needed)");
+    return ECM_B200_OK;
+}
+
+// one wave: curves [first, first+n) of the batch -> tables; runs the ecm_stage2_init program
+static int s2_wave_init(ecm_b200_ctx *c, uint32_t first, uint32_t n)
+{
+    const Stage2Program &pg = c->prog2;
+    const uint32_t T = c->eng->threads_s2;
+    c->s2_first = first; c->s2_n = n; c->s2_groups = (n + T - 1) / T;
+    c->eng->s2_setup(c->stream, c->d_state, c->G1, 2 * c->p_slot, 2 * c->p_slot + 1, SP, first, c->count, c->d_state2, c->s2_cap, c->d_tab,
+                     pg.lay.qx, pg.lay.qz, c->d_wfail);
+    CU(cudaMemcpyAsync(c->d_code, pg.init.data(), pg.init.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    return run_program(c, pg.init, c->d_code, c->d_state2, c->s2_cap, c->d_tab, c->s2_groups, n, c->d_wfail);
+}
+
+static int s2_wave_run(ecm_b200_ctx *c, const std::vector<uint64_t> &code)
+{
+    if (code.size() * 8 > c->s2_code_bytes) return fail(ECM_B200_ENOMEM, "stage-2 program larger than its buffer bound");
+    // the previous program may still be executing from d_code: the copy is ordered behind it on the same stream
+    CU(cudaMemcpyAsync(c->d_code, code.data(), code.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    return run_program(c, code, c->d_code, c->d_state2, c->s2_cap, c->d_tab, c->s2_groups, c->s2_n, c->d_wfail);
+}
+
+static void s2_wave_collect(ecm_b200_ctx *c)
+{
+    c->eng->s2_collect(c->stream, c->d_state2, c->s2_cap, c->d_wfail, c->s2_first, c->s2_n, c->count, c->d_acc, c->d_fail);
+}
+
+// device buffer bound for the program of one prime range: a range never has more instructions than
+// (#primes <= span/6 for span >= 1e5) + 1300 per window shift + ladder/window set-up
+static size_t s2_code_bound(const Stage2Params &prm, uint64_t span)
+{
+    return (size_t)(span / 6 + (span / ((uint64_t)prm.D * prm.U * 2) + 2) * 1300 + 200000) * 8;
+}
+
+int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
+{
+    int rc = s2_check_start(c, b1); if (rc) return rc;
     if (b2 <= b1) return fail(ECM_B200_EINVAL, "B2 must exceed B1 (B2 <= B1 disables stage 2, main.c:548-552)");
     CU(cudaSetDevice(c->device));
     // ---- compile (host): ecm_stage2_init now; the per-range ecm_stage2_pair programs (sieve + PAIR, about
@@ -635,82 +740,104 @@ int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
     const uint64_t PRIME_RANGE = 100000000ull;
     std::vector<std::pair<uint64_t, uint64_t>> rng;
     for (uint64_t p = b1; p < b2; p += PRIME_RANGE) rng.push_back({p, std::min(p + PRIME_RANGE, b2)});
-    std::atomic<int> nready{(int)rng.size()};
+    std::mutex mu; std::condition_variable cv; int nready = (int)rng.size();
     std::thread planner;
     if (c->prog2_b1 != b1 || c->prog2_b2 != b2) {
         plan_stage2_init(b1, c->prog2);
         c->prog2.ranges.assign(rng.size(), std::vector<uint64_t>());
         nready = 0;
         Stage2Program *pp = &c->prog2;
-        planner = std::thread([pp, rng, &nready]() {
-            for (size_t r = 0; r < rng.size(); r++) { plan_stage2_range(rng[r].first, rng[r].second, *pp, (int)r); nready.fetch_add(1, std::memory_order_release); }
+        planner = std::thread([pp, rng, &nready, &mu, &cv]() {
+            for (size_t r = 0; r < rng.size(); r++) {
+                plan_stage2_range(rng[r].first, rng[r].second, *pp, (int)r);
+                { std::lock_guard<std::mutex> lk(mu); nready++; }
+                cv.notify_all();
+            }
         });
         c->prog2_b1 = b1; c->prog2_b2 = b2;
     }
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{planner};
     const Stage2Program &pg = c->prog2;
-    const int nl = c->nl;
     const uint32_t T = c->eng->threads_s2;
-    // ---- wave size from the memory budget: tables + slot file per curve
-    const size_t per_curve = ((size_t)pg.lay.entries + c->eng->nslot_s2) * nl * 4 + 1;
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    // device buffer for the largest program: a range never has more instructions than
-    // (#primes <= span/8 for span >= 1e5) + 1300 per window shift + ladder/window set-up
     size_t code_bytes = pg.init.size() * 8;
-    for (const auto &r : rng) {
-        const uint64_t span = r.second - r.first;
-        const uint64_t bound = span / 6 + (span / ((uint64_t)pg.prm.D * pg.prm.U * 2) + 2) * 1300 + 200000;
-        code_bytes = std::max<size_t>(code_bytes, bound * 8);
-    }
-    const size_t budget = (size_t)((double)free_b * 0.90) - std::min<size_t>(code_bytes + (64u << 20), free_b / 4);
-    uint32_t cap2 = (uint32_t)std::min<size_t>((c->count + T - 1) / T * T, budget / per_curve / T * T);
-    if (cap2 < T) return fail(ECM_B200_ENOMEM, "not enough device memory for one stage-2 group");
-    if (const char *e = getenv("ECM_B200_S2_WAVE")) {        // test hook: force small waves
-        const uint32_t w = ((uint32_t)atoi(e) + T - 1) / T * T;
-        if (w >= T && w < cap2) cap2 = w;
-    }
+    for (const auto &r : rng) code_bytes = std::max(code_bytes, s2_code_bound(pg.prm, r.second - r.first));
+    uint32_t cap2 = 0;
+    rc = s2_wave_capacity(c, pg.lay.entries, code_bytes, &cap2); if (rc) return rc;
     {   // several waves: make them equal instead of one full wave plus a small remainder
         const uint32_t waves = (c->count + cap2 - 1) / cap2;
         const uint32_t even = ((c->count + waves - 1) / waves + T - 1) / T * T;
         if (even < cap2) cap2 = even;
     }
-    uint32_t *tab = nullptr, *state2 = nullptr; uint8_t *wfail = nullptr; uint64_t *d_code = nullptr;
-    auto cleanup = [&]() { cudaFree(tab); cudaFree(state2); cudaFree(wfail); cudaFree(d_code); };
-#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ECM_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
-    CUS(cudaMalloc(&tab, (size_t)pg.lay.entries * nl * 4 * cap2));
-    CUS(cudaMalloc(&state2, (size_t)c->eng->nslot_s2 * nl * 4 * cap2));
-    CUS(cudaMalloc(&wfail, cap2));
-    CUS(cudaMalloc(&d_code, code_bytes + 64));
-    if (!c->d_acc) { CUS(cudaMalloc(&c->d_acc, (size_t)nl * 4 * c->max_curves)); CUS(cudaMalloc(&c->d_fail, c->max_curves)); }
+    rc = s2_reserve(c, pg.lay.entries, cap2, code_bytes); if (rc) return rc;
+    c->s2_cap = cap2; c->s2_open = false;
     c->s2_launches = 0; c->s2_waves = 0;
-    CUS(cudaEventRecord(c->ev0, c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));
     for (uint32_t first = 0; first < c->count; first += cap2) {
-        const uint32_t n = std::min<uint32_t>(cap2, c->count - first);
-        const uint32_t groups = (n + T - 1) / T;
-        c->eng->s2_setup(c->stream, c->d_state, c->G1, 2 * c->p_slot, 2 * c->p_slot + 1, SP, first, c->count, state2, cap2, tab,
-                         pg.lay.qx, pg.lay.qz, wfail);
-        CUS(cudaMemcpyAsync(d_code, pg.init.data(), pg.init.size() * 8, cudaMemcpyHostToDevice, c->stream));
-        int rc = run_program(c, pg.init, d_code, state2, cap2, tab, groups, n, wfail);
-        if (rc) { cleanup(); return rc; }
+        rc = s2_wave_init(c, first, std::min<uint32_t>(cap2, c->count - first)); if (rc) return rc;
         for (size_t ri = 0; ri < rng.size(); ri++) {
-            while (nready.load(std::memory_order_acquire) <= (int)ri) std::this_thread::sleep_for(std::chrono::milliseconds(1));
-            const std::vector<uint64_t> &r = pg.ranges[ri];
-            if (r.size() * 8 > code_bytes) { cleanup(); return fail(ECM_B200_ENOMEM, "stage-2 program larger than its buffer bound"); }
-            CUS(cudaMemcpyAsync(d_code, r.data(), r.size() * 8, cudaMemcpyHostToDevice, c->stream));
-            rc = run_program(c, r, d_code, state2, cap2, tab, groups, n, wfail);
-            if (rc) { cleanup(); return rc; }
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return nready > (int)ri; }); }
+            rc = s2_wave_run(c, pg.ranges[ri]); if (rc) return rc;
         }
-        c->eng->s2_collect(c->stream, state2, cap2, wfail, first, n, c->count, c->d_acc, c->d_fail);
+        s2_wave_collect(c);
         c->s2_waves++;
     }
-    CUS(cudaEventRecord(c->ev1, c->stream));
-    CUS(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->s2_ms, c->ev0, c->ev1);
     c->last_ms = c->s2_ms; c->last_launches = c->s2_launches;
-#undef CUS
-    cleanup();
     c->stage2_done = true;
+    return ECM_B200_OK;
+}
+
+// ---- stage 2 at the reference's own granularity (ecm.c:67-72) -------------------------------------------------------
+// ecm_stage2_init: baby steps Pb[], their batch inversion, Pd = [w]Q for the whole batch, which must fit the device in
+// one wave (the tables stay resident for the range calls that follow).  *found_inv = 1 when an inversion met a
+// non-invertible element on some curve (the reference's return value foundDuringInv).
+int ecm_b200_stage2_init(ecm_b200_ctx *c, uint64_t b1, int *found_inv)
+{
+    int rc = s2_check_start(c, b1); if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if (c->prog2_b1 != b1 || c->prog2_b2 != 0) { plan_stage2_init(b1, c->prog2); c->prog2_b1 = b1; c->prog2_b2 = 0; }
+    const size_t code_bytes = std::max(c->prog2.init.size() * 8, s2_code_bound(c->prog2.prm, 100000000ull));
+    uint32_t cap2 = 0;
+    rc = s2_wave_capacity(c, c->prog2.lay.entries, code_bytes, &cap2); if (rc) return rc;
+    if (cap2 < c->count)
+        return fail(ECM_B200_ENOMEM, "batch does not fit one stage-2 wave on this device: use ecm_b200_stage2 (it runs waves) or a smaller batch");
+    rc = s2_reserve(c, c->prog2.lay.entries, cap2, code_bytes); if (rc) return rc;
+    c->s2_cap = cap2; c->s2_launches = 0; c->s2_waves = 1; c->s2_ms = 0;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    rc = s2_wave_init(c, 0, c->count); if (rc) return rc;
+    s2_wave_collect(c);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    std::vector<uint8_t> fl(c->count);
+    CU(cudaMemcpyAsync(fl.data(), c->d_fail, c->count, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->s2_ms += ms; c->last_ms = ms; c->last_launches = c->s2_launches;
+    if (found_inv) { *found_inv = 0; for (uint8_t f : fl) if (f) { *found_inv = 1; break; } }
+    c->s2_open = true; c->stage2_done = true;
+    return ECM_B200_OK;
+}
+
+// ecm_stage2_pair(steps, pm_v, pm_u, ...) with work->amin = amin (ecm.c:2342-2540): giant-step window from [2*amin*w]Q,
+// then the caller's pairmap -- (0,0) entries slide the window by U.  The pairmap may come from the reference's pair()
+// or from ecm_b200_pair; it is validated (EINVAL) before anything runs.
+int ecm_b200_stage2_range(ecm_b200_ctx *c, uint32_t amin, const uint32_t *pm_v, const uint32_t *pm_u, uint32_t steps)
+{
+    if (!c || (steps && (!pm_v || !pm_u))) return fail(ECM_B200_EINVAL, "null argument");
+    if (!c->s2_open) return fail(ECM_B200_ESTATE, "ecm_b200_stage2_init has not been run on this batch");
+    if (!stage2_pairmap_valid(c->prog2.prm, amin, pm_v, pm_u, steps))
+        return fail(ECM_B200_EINVAL, "pairmap leaves the stage-2 tables (window index outside [amin, amin+2L), unmapped baby step, or amin = 0)");
+    CU(cudaSetDevice(c->device));
+    c->prog2.ranges.assign(1, std::vector<uint64_t>());
+    plan_stage2_pairmap(amin, pm_v, pm_u, steps, c->prog2, 0);
+    c->prog2_b2 = 0;                                      // the cached programs no longer describe a (B1,B2) run
+    const uint32_t before = c->s2_launches;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    int rc = s2_wave_run(c, c->prog2.ranges[0]); if (rc) return rc;
+    s2_wave_collect(c);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->s2_ms += ms; c->last_ms = ms; c->last_launches = c->s2_launches - before;
     return ECM_B200_OK;
 }
 
@@ -813,6 +940,19 @@ uint64_t ecm_b200_stage2_program(uint64_t b1, uint64_t b2, int which, uint64_t *
         layout[12] = L.entries;
     }
     return src->size();
+}
+
+uint64_t ecm_b200_stage2_pairmap_program(uint64_t b1, uint32_t amin, const uint32_t *pm_v, const uint32_t *pm_u, uint32_t steps,
+                                         uint64_t *out, uint64_t cap)
+{
+    Stage2Program pg;
+    pg.prm = stage2_params(b1);
+    pg.lay = stage2_layout(pg.prm);
+    if ((steps && (!pm_v || !pm_u)) || !stage2_pairmap_valid(pg.prm, amin, pm_v, pm_u, steps)) return 0;
+    plan_stage2_pairmap(amin, pm_v, pm_u, steps, pg);
+    const std::vector<uint64_t> &src = pg.ranges.back();
+    if (out && cap >= src.size()) memcpy(out, src.data(), src.size() * 8);
+    return src.size();
 }
 
 void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R)

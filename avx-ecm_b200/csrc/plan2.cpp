@@ -66,7 +66,7 @@ struct Asm {
 void ladder(Asm &a, const Stage2Layout &L, uint64_t c, uint64_t &ptadds)
 {
     a.ldpt(PU, L.qx, L.qz);
-    if (c == 1) return;
+    if (c <= 1) return;          // c = 0 cannot be reached: callers reject amin = 0 (stage2_pairmap_valid, ecm_b200_stage2)
     a.sums1(PU);
     a.vdup(S1_, D1_, T1_, PV);                     // x2 = 2Q
     if (c == 2) { a.copy(UX, VX); a.copy(UZ, VZ); return; }
@@ -182,6 +182,32 @@ void plan_stage2_init(uint64_t b1, Stage2Program &prog)
 // ecm_stage2_pair (ecm.c:2342-2540) for the primes of [lo,hi)
 void plan_stage2_range(uint64_t lo, uint64_t hi, Stage2Program &prog, int index)
 {
+    std::vector<uint32_t> pm_v, pm_u;
+    uint32_t amin_final = 0, npairs = 0;
+    const uint32_t steps = pair_plan(lo, hi, prog.prm, pm_v, pm_u, &amin_final, &npairs);
+    const uint32_t w = prog.prm.D;
+    plan_stage2_pairmap((uint32_t)((lo + w) / (2 * (uint64_t)w)), pm_v.data(), pm_u.data(), steps, prog, index);
+}
+
+// Is (amin, pairmap) something ecm_stage2_pair could execute without leaving its tables?  (A caller-made pairmap is
+// data from outside; the reference trusts it, a device program must not.)
+bool stage2_pairmap_valid(const Stage2Params &p, uint32_t amin, const uint32_t *pm_v, const uint32_t *pm_u, uint32_t steps)
+{
+    if (amin == 0) return false;                      // A - w would be negative: B1 below D (the reference aborts there)
+    const std::vector<uint32_t> map = stage2_map(p, nullptr);
+    const uint32_t win = 2 * p.L;
+    uint64_t a = amin;
+    for (uint32_t k = 0; k < steps; k++) {
+        if (pm_u[k] == 0 && pm_v[k] == 0) { a += p.U; continue; }
+        if (pm_v[k] < a || pm_v[k] - a >= win) return false;
+        if (pm_u[k] >= map.size() || map[pm_u[k]] == 0) return false;
+    }
+    return a < (1ull << 32);
+}
+
+// ecm_stage2_pair for a given starting amin and pairmap (the reference's own arguments, ecm.c:2342-2351)
+void plan_stage2_pairmap(uint32_t amin, const uint32_t *pm_v, const uint32_t *pm_u, uint32_t steps, Stage2Program &prog, int index)
+{
     const Stage2Params &p = prog.prm;
     const Stage2Layout &L = prog.lay;
     const std::vector<uint32_t> map = stage2_map(p, nullptr);
@@ -189,13 +215,8 @@ void plan_stage2_range(uint64_t lo, uint64_t hi, Stage2Program &prog, int index)
     if (index < 0) { prog.ranges.emplace_back(); index = (int)prog.ranges.size() - 1; }
     prog.ranges[index].clear();
     Asm a{prog.ranges[index]};
-
-    std::vector<uint32_t> pm_v, pm_u;
-    uint32_t amin_final = 0, npairs = 0;
-    const uint32_t steps = pair_plan(lo, hi, p, pm_v, pm_u, &amin_final, &npairs);
     prog.pairmap_steps += steps;
 
-    uint32_t amin = (uint32_t)((lo + w) / (2 * (uint64_t)w));
     const uint64_t A = (uint64_t)amin * w * 2;
     // the window is a ring of `win` table entries: logical index i lives at ring[(base+i) % win]
     uint32_t base = 0;

@@ -56,5 +56,9 @@ void plan_stage2_init(uint64_t b1, Stage2Program &prog);
 // prog.ranges[index] (index < 0: append).  Ranges may be compiled by a background thread while the GPU
 // executes the previous one; the counters are only meaningful once all ranges are done.
 void plan_stage2_range(uint64_t lo, uint64_t hi, Stage2Program &prog, int index = -1);
+// the same for a caller-supplied pairmap starting at window index amin (ecm_stage2_pair's own arguments,
+// ecm.c:2342-2351); validate untrusted pairmaps with stage2_pairmap_valid first
+void plan_stage2_pairmap(uint32_t amin, const uint32_t *pm_v, const uint32_t *pm_u, uint32_t steps, Stage2Program &prog, int index = -1);
+bool stage2_pairmap_valid(const Stage2Params &p, uint32_t amin, const uint32_t *pm_v, const uint32_t *pm_u, uint32_t steps);
 
 }  // namespace ecmb200

@@ -54,6 +54,27 @@ int main(void)
             if (flag[i]) for (k = Lm - 1; k >= 0; k--) printf("%08x", g[(size_t)k * 8 + i]);
             printf("\n");
         }
+        /* the same stage 2 at the reference's own granularity (ecm.c:67-72, driver loop ecm.c:1400-1476): init once,
+         * then one range call per pairmap -- here the pairmap of ecm_b200_pair, where a maintainer would pass pair()'s */
+        {
+            uint32_t amin_final, npairs, steps, *pm_v, *pm_u, *g2 = (uint32_t *)calloc((size_t)Lm * 8, 4);
+            uint8_t flag2[8];
+            int found_inv = -1;
+            ecm_b200_stage2_params(20000, &D, &U, &L, &R);
+            steps = ecm_b200_pair(20000, 2000000, D, U, NULL, NULL, 0, &amin_final, &npairs);
+            pm_v = (uint32_t *)malloc((size_t)steps * 4 + 4); pm_u = (uint32_t *)malloc((size_t)steps * 4 + 4);
+            ecm_b200_pair(20000, 2000000, D, U, pm_v, pm_u, steps, &amin_final, &npairs);
+            if (ecm_b200_build_curves(ctx, 8, sigma) || ecm_b200_stage1(ctx, 20000) || ecm_b200_stage2_init(ctx, 20000, &found_inv) ||
+                ecm_b200_stage2_range(ctx, (20000 + D) / (2 * D), pm_v, pm_u, steps) || ecm_b200_read_stage2(ctx, NULL, flag2, g2, NULL)) {
+                printf("stage2_init/range failed: %s\n", ecm_b200_last_error());
+                return 6;
+            }
+            if (memcmp(flag, flag2, 8) || memcmp(g, g2, (size_t)Lm * 8 * 4)) { printf("stage2_init/range disagrees with stage2\n"); return 7; }
+            pm_v[steps / 2] += 1000;                        /* a pairmap that leaves the window must be refused, not executed */
+            if (ecm_b200_stage2_range(ctx, (20000 + D) / (2 * D), pm_v, pm_u, steps) != ECM_B200_EINVAL) { printf("bad pairmap accepted\n"); return 8; }
+            printf("stage2_init + stage2_range(%u steps, %u pairs): identical factors, foundDuringInv = %d\n", steps, npairs, found_inv);
+            free(pm_v); free(pm_u); free(g2);
+        }
         free(g);
     }
     ecm_b200_destroy(ctx);

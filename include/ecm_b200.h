@@ -100,6 +100,19 @@ int ecm_b200_read_stage1(ecm_b200_ctx *ctx, uint32_t *x, uint32_t *z, uint8_t *f
  * ecm.c:2342-2540 driven by pair() ecm.c:2559-2910).  Runs the pairing continuation over all
  * primes in [b1, b2) in the reference's 1e8 ranges, D and U as the reference selects them.     */
 int ecm_b200_stage2(ecm_b200_ctx *ctx, uint64_t b1, uint64_t b2);
+/* The same continuation at the reference's own granularity (ecm.c:67-72), for a host that keeps avx-ecm's driver loop
+ * (ecm.c:1400-1476) and its pair():
+ *   ecm_b200_stage2_init   replaces  int foundDuringInv = ecm_stage2_init(P, mdata, work, verbose)   (ecm.c:2201-2340)
+ *   ecm_b200_stage2_range  replaces  ecm_stage2_pair(steps, pm_v, pm_u, P, mdata, work, verbose) with work->amin = amin
+ *                                    (ecm.c:2342-2540)
+ * init builds the baby-step table for the whole batch, which must fit the device in one wave (ECM_B200_ENOMEM
+ * otherwise: ecm_b200_stage2 runs such batches in waves); the tables stay resident until the curves are rebuilt.
+ * pm_v/pm_u are pair()'s pairmap_v/pairmap_u (ecm.c:2559-2910; ecm_b200_pair produces the same arrays): entry
+ * (0,0) slides the giant-step window by U, any other entry multiplies the accumulator by Pa[pm_v-amin] - Pb[map[pm_u]].
+ * A pairmap that would leave the tables is rejected with ECM_B200_EINVAL.  ecm_b200_read_stage2 may be called after
+ * init and after every range.                                                                                        */
+int ecm_b200_stage2_init(ecm_b200_ctx *ctx, uint64_t b1, int *found_inv);
+int ecm_b200_stage2_range(ecm_b200_ctx *ctx, uint32_t amin, const uint32_t *pm_v, const uint32_t *pm_u, uint32_t steps);
 /* acc: stage-2 accumulator out of Montgomery form; factor_flag/gcd_out as above for gcd(acc,N)
  * (ecm.c:1485-1497); inv_fail[i] = 1 when curve i met a non-invertible element.                */
 int ecm_b200_read_stage2(ecm_b200_ctx *ctx, uint32_t *acc, uint8_t *factor_flag, uint32_t *gcd_out, uint8_t *inv_fail);
@@ -126,6 +139,10 @@ uint64_t ecm_b200_plan_stage2(uint64_t b1, uint64_t b2, uint64_t *counts);
  * hi = imm; op codes and slot numbers are listed in avx-ecm_b200/csrc/plan2.hpp.  layout[0..12] = npb,
  * table bases pbx, pbz, pba, pax, paz, pai, paa, qx, qz, pdx, pdz, total entries.  Returns the length. */
 uint64_t ecm_b200_stage2_program(uint64_t b1, uint64_t b2, int which, uint64_t *out, uint64_t cap, uint32_t *layout);
+/* The program ecm_b200_stage2_range would run for (amin, pairmap) with the geometry of b1; returns its length,
+ * 0 when the pairmap is rejected (it would leave the tables).  For CPU-side checking, no GPU needed.      */
+uint64_t ecm_b200_stage2_pairmap_program(uint64_t b1, uint32_t amin, const uint32_t *pm_v, const uint32_t *pm_u, uint32_t steps,
+                                         uint64_t *out, uint64_t cap);
 /* Stage-2 geometry chosen for B1 (thread_init, main.c:834-970): D, U, L, R.                    */
 void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R);
 

@@ -13,7 +13,7 @@
  * 4712-4721), so the sequence of *true* residues is independent of R and of
  * the limb width; this file tracks the true residues directly.
  *
- * Parity: PINNED.  tests/test_oracle_vs_ref.py checks it byte-for-byte against
+ * Parity: PINNED.  tests/test_oracle_vs_golden.py checks it byte-for-byte against
  * save_b1.txt produced by the compiled reference (oracle/_ref, built by
  * oracle/build_ref.sh) and against the factors/sigmas in the reference's
  * test_inputs.txt / test.csh; tests/golden/ holds the committed vectors.

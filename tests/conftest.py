@@ -28,6 +28,21 @@ def composites():
 
 GOLDEN = golden_cases()
 
+# Full-size known answers (test.csh / test_t35.csh lines and the README example at the reference's own B1/B2): tens of
+# seconds each for 8 curves on one warp, so the GPU suite runs them all at once (tests/test_gpu_known_answers.py)
+# instead of one by one through the per-case tests; "slow_" cases (huge B1 / huge B2 / 1165-bit input) only run with
+# ECM_B200_SLOW=1, on the CPU oracle as well as on the GPU.
+SLOW = os.environ.get("ECM_B200_SLOW", "") not in ("", "0")
+
+
+def is_known_answer(name):
+    # ... plus the two wide synthetic cases at a B1 that is not a toy (8 curves x 2048 bits: ~20 s per stage on one warp)
+    return name.startswith(("readme508_b1_1e6", "t35_full_", "csh_line", "slow_csh_line", "syn1024_b1_1e5", "syn2048_b1_5e4"))
+
+
+def is_slow(name):
+    return name.startswith("slow_")
+
 
 def golden_factor(g, sigma, stage):
     for f in g["factors"]:

@@ -159,3 +159,39 @@ def test_planners_match_oracle_on_random_bounds():
         hi = lo + rng.randrange(1, 2000000)
         D, U, L, R = E.stage2_params(b1)
         assert E.pair(lo, hi, D) == O.pair(lo, hi, D), (lo, hi, D)
+
+
+@pytest.mark.parametrize("b1,b2", [(3000, 300000), (50000, 5000000), (2000, 100100000)])
+def test_caller_pairmap_compiles_to_the_range_program(b1, b2):
+    """ecm_b200_stage2_range takes the reference's own arguments (steps, pm_v, pm_u with work->amin, ecm.c:2342-2351).
+    Fed with the ORACLE's pair() output -- the arrays a maintainer who keeps the reference's pair() would pass -- it must
+    compile to exactly the program ecm_b200_stage2 runs for the same prime range."""
+    D, U, L, R = E.stage2_params(b1)
+    lo = b1
+    which = 0
+    while lo < b2:
+        hi = min(lo + 100000000, b2)
+        v, u, amin_final, npairs = O.pair(lo, hi, D)
+        amin = (lo + D) // (2 * D)
+        prog = E.stage2_pairmap_program(b1, amin, v, u)
+        ref, _ = E.stage2_program(b1, b2, which)
+        assert prog == ref and len(prog) > 0
+        lo, which = hi, which + 1
+
+
+def test_bad_pairmaps_are_rejected():
+    b1 = 3000
+    D, U, L, R = E.stage2_params(b1)
+    v, u, _, _ = O.pair(b1, 300000, D)
+    amin = (b1 + D) // (2 * D)
+    k = next(i for i in range(len(v)) if v[i] or u[i])
+    assert E.stage2_pairmap_program(b1, amin, v, u)
+    assert E.stage2_pairmap_program(b1, 0, v, u) == []                              # A - w < 0
+    bad = list(v); bad[k] = amin + 2 * L                                            # beyond the giant-step window
+    assert E.stage2_pairmap_program(b1, amin, bad, u) == []
+    bad = list(v); bad[k] = amin - 1 if amin else 0
+    assert E.stage2_pairmap_program(b1, amin + 1, bad, u) == []                     # before the window
+    bad = list(u); bad[k] = U * (D + 1) + 3                                         # outside the baby-step map
+    assert E.stage2_pairmap_program(b1, amin, v, bad) == []
+    bad = list(u); bad[k] = 5                                                       # 5 | D for every D: baby step 5 is not stored
+    assert E.stage2_pairmap_program(b1, amin, v, bad) == []

@@ -1,7 +1,7 @@
 """GPU parity of curve construction + stage 1 against the golden vectors of the compiled
 reference (byte-identical save_b1.txt lines) and against the oracle, through the C ABI."""
 import pytest
-from conftest import GOLDEN, golden_factor, golden_base, composites
+from conftest import GOLDEN, golden_factor, golden_base, composites, is_known_answer
 import oracle_lib as O
 import avx_ecm_b200 as E
 
@@ -11,7 +11,8 @@ MAXBITS = 2048
 
 
 def usable(g):
-    return int(g["n"]).bit_length() <= MAXBITS and g["b1"] <= 100000000      # B1 > 1e8: hours for 8 curves on one warp
+    # B1 > 1e8: hours for 8 curves on one warp; full-size known answers run concurrently in test_gpu_known_answers.py
+    return int(g["n"]).bit_length() <= MAXBITS and g["b1"] <= 100000000 and not is_known_answer(g["name"])
 
 
 @pytest.mark.parametrize("name", sorted(k for k, g in GOLDEN.items() if usable(g)))

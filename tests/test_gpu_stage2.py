@@ -2,7 +2,7 @@
 vectors of the compiled reference: the stage-2 accumulator of every curve (true residue), the
 factors reported in stage 1 and stage 2, and the op counters.  Through the C ABI."""
 import pytest
-from conftest import GOLDEN, golden_factor, golden_base, composites
+from conftest import GOLDEN, golden_factor, golden_base, composites, is_known_answer
 import oracle_lib as O
 import avx_ecm_b200 as E
 
@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def usable(g):
-    return int(g["n"]).bit_length() <= 2048 and g["b2"] > g["b1"]
+    return int(g["n"]).bit_length() <= 2048 and g["b2"] > g["b1"] and not is_known_answer(g["name"])
 
 
 @pytest.mark.parametrize("name", sorted(k for k, g in GOLDEN.items() if usable(g)))
@@ -156,3 +156,110 @@ def test_cli_on_two_gpus_writes_the_single_gpu_files(tmp_path, monkeypatch):
         subprocess.run([cli, str(N), "10", "5000", gpus, "5000", "424242"], cwd=d, capture_output=True, text=True, check=True)
         outs.append(((d / "checkpoint.txt").read_text(), (d / "save_b1.txt").read_text()))
     assert outs[0] == outs[1] and outs[0][0].count("\n") == 20
+
+
+def test_stage2_at_the_reference_granularity_with_oracle_pairmaps():
+    """ecm_b200_stage2_init / ecm_b200_stage2_range (the reference's ecm_stage2_init -> foundDuringInv and
+    ecm_stage2_pair(steps, pm_v, pm_u), ecm.c:67-72) driven like vececm's loop (ecm.c:1400-1476) with the pairmaps of
+    the ORACLE's pair(): two prime ranges, accumulators read after init, after each range, equal to ecm_b200_stage2
+    and to the oracle."""
+    N = composites()["syn415"]
+    b1, b2, sig = 2000, 100100000, [7, 8, 9, 2 ** 63 + 11]       # the golden syn415_two_ranges covers sigma 7..14
+    D, U, L, R = E.stage2_params(b1)
+    ctx = E.EcmContext(N, len(sig))
+    try:
+        ctx.build_curves(sig); ctx.stage1(b1)
+        assert ctx.stage2_init(b1) is False
+        acc0, _, fail0 = ctx.read_stage2()
+        assert acc0 == [1] * len(sig) and fail0 == [0] * len(sig)               # acc = one (ecm.c:2318)
+        lo = b1
+        while lo < b2:
+            hi = min(lo + 100000000, b2)
+            v, u, _, _ = O.pair(lo, hi, D)
+            ctx.stage2_range((lo + D) // (2 * D), v, u)
+            lo = hi
+        acc, f2, fail = ctx.read_stage2()
+        with pytest.raises(E.EcmError, match="pairmap leaves"):
+            ctx.stage2_range(0, v, u)
+        ctx.build_curves(sig); ctx.stage1(b1)
+        with pytest.raises(E.EcmError, match="stage2_init has not been run"):
+            ctx.stage2_range((b1 + D) // (2 * D), v, u)
+        ctx.stage2(b1, b2)
+        assert ctx.read_stage2() == (acc, f2, fail)
+    finally:
+        ctx.close()
+    for i, s in enumerate(sig):
+        assert acc[i] == O.ecm_curve(N, b1, b2, s)["acc"]
+    g = GOLDEN["syn415_two_ranges"]
+    assert acc[:3] == [int(a, 16) for a in g["acc_true_hex"][:3]]
+
+
+def test_stage2_init_reports_found_during_inv():
+    g = GOLDEN["small96_D210"]                                   # tiny composite: inversions fail on some curves
+    N, b1, s0 = int(g["n"]), g["b1"], int(g["sigma0"])
+    ctx = E.EcmContext(N, 8)
+    try:
+        ctx.build_curves([s0 + i for i in range(8)]); ctx.stage1(b1)
+        found = ctx.stage2_init(b1)
+        _, _, fail = ctx.read_stage2()
+        assert found == any(fail)
+        D = E.stage2_params(b1)[0]
+        v, u, _, _ = O.pair(b1, g["b2"], D)
+        ctx.stage2_range((b1 + D) // (2 * D), v, u)
+        acc, f2, fail = ctx.read_stage2()
+    finally:
+        ctx.close()
+    assert any(fail) and g["inv_fail_gcd_calls"] > 0
+    for i in range(8):
+        assert f2[i] == golden_factor(g, s0 + i, 2)
+        if not fail[i] or i == 0:
+            assert acc[i] == int(g["acc_true_hex"][i], 16)
+
+
+def test_stage2_state_checks_and_resume_from_loaded_points():
+    N = composites()["syn415"]
+    sig = [7, 8, 9]
+    ctx = E.EcmContext(N, 200)
+    try:
+        ctx.build_curves(list(range(100, 300)))
+        ctx.stage1_begin(20000)
+        ctx.stage1_step(1)                                       # stage 1 only partly run
+        with pytest.raises(E.EcmError, match="still in progress"):
+            ctx.stage2(20000, 2000000)
+        with pytest.raises(E.EcmError, match="still in progress"):
+            ctx.stage1_range(20000, 0)
+        with pytest.raises(E.EcmError, match="still in progress"):
+            ctx.stage1_begin(20000)
+        ctx.build_curves(sig); ctx.stage1(3000)
+        with pytest.raises(E.EcmError, match="B1 too small"):
+            ctx.stage2(20, 2000)                                 # amin = 0: the reference aborts in next_pt_vec
+        x, z, _ = ctx.read_stage1()
+        ctx.stage2(3000, 300000)
+        acc = ctx.read_stage2()[0]
+        # resume: the stage-1 points of a save_b1.txt file loaded as X/Z with the curve parameter, then stage 2 only
+        # (GMP-ECM's -resume work flow); stage 2 normalises every table entry, so the accumulator is the same
+        xs = [xi * pow(zi, -1, N) % N for xi, zi in zip(x, z)]
+        ss = [O.build_curve(N, s)[1] for s in sig]
+        ctx.load_curves(xs, ss, sig)
+        ctx.stage2(3000, 300000)
+        assert ctx.read_stage2()[0] == acc
+    finally:
+        ctx.close()
+
+
+def test_cli_random_sigmas_are_valid_resume_lines(tmp_path):
+    """sigma omitted / 0: the CLI draws sigmas with the reference's LCG, all >= 6 (ecm.c:1564-1570, main.c:757-763);
+    every save_b1.txt line must still be the stage-1 point of the curve it names."""
+    import os, re, subprocess
+    from conftest import ROOT
+    from test_resume_lines_cpu import check_line
+    N = composites()["t35"]
+    cli = os.path.join(ROOT, "avx-ecm_b200", "avx-ecm-b200")
+    for args in ([str(N), "12", "3000", "1", "3000"], [str(N), "12", "3000", "1", "3000", "0"]):
+        d = tmp_path / ("r%d" % len(args))
+        d.mkdir()
+        subprocess.run([cli] + args, cwd=d, capture_output=True, text=True, check=True)
+        lines = (d / "save_b1.txt").read_text().splitlines(keepends=True)
+        sig = [int(re.search(r"SIGMA=(\d+)", l).group(1)) for l in lines]
+        assert len(lines) == 12 and len(set(sig)) == 12 and min(sig) >= 6
+        assert [check_line(l, expect_n=N) for l in lines] == ["ok"] * 12

@@ -84,9 +84,36 @@ def composites():
     }
 
 
+def csh_line(k):
+    """Line k (1-based) of the reference's own regression script test.csh: (N, curves, B1, B2, sigma).  Expressions
+    are evaluated here with Python integers (the calc.c grammar of these lines is + - * / ^ ! and parentheses)."""
+    from math import factorial  # noqa: F401  (used by eval below)
+    lines = [l for l in open("/root/reference/test.csh") if l.startswith("./avx-ecm")]
+    m = re.match(r"./avx-ecm\s+(\"[^\"]+\"|'[^']+'|\S+)\s+(\d+)\s+(\d+)\s+(\d+)\s+(\d+)\s+(\d+)", lines[k - 1])
+    e = m.group(1).strip("\"'").replace("^", "**").replace("/", "//")
+    e = re.sub(r"(\d+)!", r"factorial(\1)", e)
+    return (eval(e), int(m.group(2)), int(m.group(3)), int(m.group(5)), int(m.group(6)))
+
+
 def cases():
     c = composites()
-    return [
+    extra = [
+        # BASELINE config [0]: the README example at full size; sigma 1007 (lane 7) finds 272602401466814027129 in stage 1
+        ("readme508_b1_1e6", c["readme508"], 8, 1000000, 100000000, 1000),
+        # test_t35.csh: the two other survey-verified stage-2 hits, full size
+        ("t35_full_sigma_11919771003873180376", c["t35"], 8, 1000000, 100000000, 11919771003873180376),
+        ("t35_full_sigma_10019108749973911965", c["t35"], 8, 1000000, 100000000, 10019108749973911965),
+        # wider operands at a B1 that is not a toy
+        ("syn1024_b1_1e5", c["syn1024"], 8, 100000, 10000000, 7),
+        ("syn2048_b1_5e4", c["syn2048"], 8, 50000, 5000000, 7),
+    ]
+    # more lines of test.csh (default GPU suite: B1 <= 3e6, B2 <= 1.05e9)
+    for k in (2, 9, 11, 12, 13, 14, 19, 22, 25):
+        extra.append(("csh_line%02d" % k,) + csh_line(k))
+    # slow ones (ECM_B200_SLOW=1 on the GPU): 1165-bit input, "huge B1", "huge B2"  (test.csh:7, 33-37)
+    for k in (7, 26, 27):
+        extra.append(("slow_csh_line%02d" % k,) + csh_line(k))
+    return extra + [
         # name, N, curves, B1, B2, sigma0
         ("readme508_b1_5e4", c["readme508"], 8, 50000, 5000000, 1000),
         ("syn415_b1_1e5", c["syn415"], 8, 100000, 10000000, 7),
