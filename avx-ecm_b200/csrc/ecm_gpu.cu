@@ -229,6 +229,8 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
     // reference R: MAXBITS = smallest multiple of 208 strictly above bitlen(N) (main.c:465-483)
     uint32_t maxbits_ref = 208; while (maxbits_ref <= bitlen(c->n)) maxbits_ref += 208;
     Big rri = one; for (uint32_t i = 0; i < maxbits_ref; i++) half_mod(rri, c->n);   // R * 2^-MAXBITS mod N
+    Big rref(nl, 0); rref[0] = 1;
+    for (uint32_t i = 0; i < maxbits_ref; i++) dbl_mod(rref, c->n);                  // 2^MAXBITS mod N, a plain integer
     c->chk = c->n;
     if (fold) {                                           // plain residues: "R = 1"
         one.assign(nl, 0); one[0] = 1;
@@ -236,13 +238,14 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
     }
     if (chk) {                                            // special form: plain residues, R_ref = 1
         rri = one;
+        rref.assign(nl, 0); rref[0] = 1;
         c->chk.assign(nl, 0);
         for (int i = 0; i < chklimbs; i++) c->chk[i] = chk[i];
         c->special = true;
     }
     uint32_t inv = 1; for (int i = 0; i < 5; i++) inv *= 2 - c->n[0] * inv;           // N^-1 mod 2^32
     const uint32_t m0inv = 0u - inv;
-    eng->set_params(c->n, one, r2, r3, rri, m0inv);
+    eng->set_params(c->n, one, r2, r3, rri, rref, m0inv);
     if (fold) eng->set_special(sp_kind, sp_k, sp_c);
     c->fold = fold;
 

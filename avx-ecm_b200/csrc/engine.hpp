@@ -16,7 +16,7 @@ struct Engine {
     virtual int stride_for_threads(uint32_t T) const = 0;
     size_t params_bytes = 0;
     virtual ~Engine() {}
-    virtual void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, uint32_t m0inv) = 0;
+    virtual void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, const Big &rref, uint32_t m0inv) = 0;
     // special-form engines (make_engine_sp_*): n = 2^kbits - cval (kind > 0) or 2^kbits + 1 (kind < 0); residues are plain
     virtual void set_special(int kind, uint32_t kbits, uint32_t cval) = 0;
     virtual bool serves_special(uint32_t kbits) const = 0;   // is bit kbits inside the word range this kernel set folds at

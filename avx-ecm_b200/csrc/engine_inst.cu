@@ -19,9 +19,9 @@ struct EngineT : Engine {
         params_bytes = sizeof(ModParams<NL>);
         threads_s2 = S2Cfg<NL>::THREADS; smem_s2 = S2Cfg<NL>::smem; nslot_s2 = NSLOT_S2;
     }
-    void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, uint32_t m0inv) override
+    void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, const Big &rref, uint32_t m0inv) override
     {
-        for (int k = 0; k < NL; k++) { P.n[k] = n[k]; P.one[k] = one[k]; P.r2[k] = r2[k]; P.r3[k] = r3[k]; P.rrefinv[k] = rri[k]; }
+        for (int k = 0; k < NL; k++) { P.n[k] = n[k]; P.one[k] = one[k]; P.r2[k] = r2[k]; P.r3[k] = r3[k]; P.rrefinv[k] = rri[k]; P.rref[k] = rref[k]; }
         P.m0inv = m0inv; P.kind = 0; P.kbits = 0; P.cval = 0;
     }
     void set_special(int kind, uint32_t kbits, uint32_t cval) override { P.kind = kind; P.kbits = kbits; P.cval = cval; }

@@ -299,6 +299,38 @@ enum : uint32_t { V2_ACC = 6, V2_SP = 11, NSLOT_S2 = 14, NGLOBAL_S2 = 7 };   // 
 // vectors does (ecm.c:1925-1949 with insert_mpz_to_vec main.c:117-138): the accumulator becomes the
 // raw gcd and the "inverse" is the raw, un-inverted product -- as Montgomery-domain values of the
 // reference (R_ref = 2^MAXBITS) these are g/R_ref and x/R_ref.
+// Successful inversions reproduce one more accident of the reference, "stale high words": the vector lane that receives
+// the new value v = x^-1 * R_ref mod N still holds the operand x taken out of Montgomery form (ecm.c:1903-1911), and
+// insert_mpz_to_vec (main.c:117-138) only writes the 52-bit words of v up to its top non-zero one -- words of x above
+// the length of v survive.  The lane then holds v + (x with its low 52k bits cleared), k = 52-bit words of v, and the
+// reference computes on with that residue.  With b bits in the top word of N this hits about 2^-b of all inversions:
+// never in practice for most inputs, constantly when N is one bit longer than a multiple of 52 (test.csh lines 2 and
+// 25: 729- and 417-bit inputs, golden cases csh_line02 / csh_line25).  Pg->rref = R_ref mod N as a plain integer
+// (1 for special-form inputs, whose residues are plain), Pg->rrefinv = R_ref^-1 in Montgomery form.
+template <int NL>
+__device__ __noinline__ void stale_high_words(uint32_t *t, const uint32_t *xmont, const ModParams<NL> *Pg)
+{
+    uint32_t v[NL], xp[NL], one[NL];
+    for (int k = 0; k < NL; k++) one[k] = (k == 0);
+    nm_mul<NL>(v, t, Pg->rref, Pg);                      // x^-1 R * R_ref / R = v (plain, canonical)
+    nm_mul<NL>(xp, xmont, one, Pg);                      // x (plain)
+    int bl = 0;
+    for (int k = NL - 1; k >= 0; k--) if (v[k]) { bl = 32 * k + 32 - __clz(v[k]); break; }
+    const int cut = 52 * ((bl + 51) / 52);               // bits of v's 52-bit words
+    bool any = false;
+    for (int k = 0; k < NL; k++) {
+        uint32_t w = xp[k];
+        if (32 * k + 32 <= cut) w = 0;
+        else if (32 * k < cut) w &= ~0u << (cut - 32 * k);
+        xp[k] = w;
+        any |= (w != 0);
+    }
+    if (!any) return;                                    // the usual case: nothing survives
+    nm_addsub<NL>(v, v, xp, false, Pg);                  // (v + stale) mod N; v + stale < 2N
+    nm_mul<NL>(v, v, Pg->r2, Pg);
+    nm_mul<NL>(t, v, Pg->rrefinv, Pg);                   // back: (v + stale) / R_ref in Montgomery form
+}
+
 template <int NL, int STRIDE>
 __device__ __noinline__ void vm2_inverse(uint32_t *dptr, const uint32_t *xptr, uint32_t *accptr, const ModParams<NL> *Pg, uint8_t *fail_flag)
 {
@@ -307,6 +339,7 @@ __device__ __noinline__ void vm2_inverse(uint32_t *dptr, const uint32_t *xptr, u
     const bool ok = nm_inverse<NL>(inv, g, a, Pg);
     if (ok) {
         nm_mul<NL>(t, inv, Pg->r3, Pg);                   // (xR)^-1 * R^3 * R^-1 = x^-1 R
+        stale_high_words<NL>(t, a, Pg);
     } else {
         *fail_flag = 1;
         nm_mul<NL>(t, g, Pg->r2, Pg);                     // g in Montgomery form

@@ -56,6 +56,8 @@ struct ModParams {
     uint32_t r3[NL];     // R^3 mod N        (fix-up after a raw modular inverse)
     uint32_t rrefinv[NL];// (2^-MAXBITS_ref) * R mod N : Montgomery form of the reference's R^-1, used
                          // only on the inversion-failure path (see vm.cuh op INV)
+    uint32_t rref[NL];   // the reference's R = 2^MAXBITS_ref mod N as a plain integer (1 for special-form inputs): only for
+                         // the stale-high-words emulation of the stage-2 inversion (kernels.cuh)
     uint32_t m0inv;      // -N^-1 mod 2^32   (monty.vrho, main.c:637-640)
     // special-form base (only read by the ECM_SPECIAL kernels): N = 2^kbits - cval (kind > 0) or 2^kbits + 1 (kind < 0)
     int32_t kind;

@@ -49,6 +49,7 @@ typedef struct {
     uint32_t npb;
     int found_inv;                    /* any inversion failure seen           */
     mpz_t rref_inv;                   /* 2^-MAXBITS mod N, MAXBITS of the 52-bit build (main.c:465-483) */
+    unsigned long maxbits_ref;        /* that MAXBITS; 0 for special-form inputs (plain residues) */
     mpz_t nchk;                       /* modulus of the factor checks: n, or the input cofactor (nhat) in Mersenne mode */
 } owork;
 
@@ -418,6 +419,29 @@ static int batch_invert(owork *w, opt *pts, mpz_t *out, mpz_t *A, int start, int
         fmul(w, w->acc, g, w->rref_inv);
         fmul(w, B[num - 1], A[num - 1], w->rref_inv);
         found = 1;
+    } else {
+        /* Stale high words (ecm.c:1913-1946 with insert_mpz_to_vec, main.c:117-138): the vector lane that receives the
+         * inverse still holds the operand a = A[num-1] taken out of Montgomery form (ecm.c:1903-1911), and
+         * insert_mpz_to_vec only writes the words of its source that are non-zero from the top -- the 52-bit words of
+         * a above the length of the new value v = a^-1 * 2^MAXBITS mod N stay where they are.  The lane then holds
+         * v + (a with its low 52k bits cleared), k = words of v, and the reference computes on with that residue.
+         * With b bits in the top word of N this happens to about 2^-b of all inversions: never in practice for most
+         * inputs, constantly when N is one bit longer than a multiple of 52 (test.csh lines 2 and 25: 729 and 417 bits). */
+        size_t k;
+        mpz_mul_2exp(g, B[num - 1], w->maxbits_ref);         /* v (special-form inputs: maxbits_ref = 0, plain values) */
+        mpz_mod(g, g, w->n);
+        k = (mpz_sizeinbase(g, 2) + 51) / 52;
+        if (mpz_sgn(g) == 0) k = 0;
+        {
+            mpz_t stale; mpz_init(stale);
+            mpz_tdiv_q_2exp(stale, A[num - 1], 52 * k);
+            if (mpz_sgn(stale) != 0) {
+                mpz_mul_2exp(stale, stale, 52 * k);
+                mpz_add(g, g, stale);
+                fmul(w, B[num - 1], g, w->rref_inv);
+            }
+            mpz_clear(stale);
+        }
     }
     for (i = num - 2; i >= 0; i--) fmul(w, B[i], pts[start + i + 1].Z, B[i + 1]);
     for (i = 0; i < num; i++) {
@@ -647,11 +671,13 @@ static owork *work_new2(const char *n_hex, const char *m_hex)
     if (m_hex) {
         if (mpz_set_str(w->n, m_hex, 16) != 0) { free(w); return NULL; }
         mpz_init(w->rref_inv); mpz_set_ui(w->rref_inv, 1);      /* failure lanes keep plain g and a (ecm.c:1903-1946) */
+        w->maxbits_ref = 0;
     } else {   /* main.c:465-483: MAXBITS = smallest multiple of 208 strictly above bitlen(N) */
         unsigned long maxbits = 208;
         mpz_set(w->n, w->nchk);
         mpz_init(w->rref_inv);
         while (maxbits <= mpz_sizeinbase(w->n, 2)) maxbits += 208;
+        w->maxbits_ref = maxbits;
         mpz_set_ui(w->rref_inv, 1); mpz_mul_2exp(w->rref_inv, w->rref_inv, maxbits);
         if (mpz_invert(w->rref_inv, w->rref_inv, w->n) == 0) mpz_set_ui(w->rref_inv, 0);
     }
