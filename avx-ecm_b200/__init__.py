@@ -72,6 +72,7 @@ def lib():
         "ecm_b200_plan_stage2": (c.c_uint64, [c.c_uint64, c.c_uint64, u64p]),
         "ecm_b200_stage2_program": (c.c_uint64, [c.c_uint64, c.c_uint64, c.c_int, u64p, c.c_uint64, u32p]),
         "ecm_b200_stage2_pairmap_program": (c.c_uint64, [c.c_uint64, c.c_uint32, u32p, u32p, c.c_uint32, u64p, c.c_uint64]),
+        "ecm_b200_rv_program": (c.c_int, [c.c_int, u32p, c.c_int]),
         "ecm_b200_pair": (c.c_uint32, [c.c_uint64, c.c_uint64, c.c_uint32, c.c_uint32, u32p, u32p, c.c_uint32, u32p, u32p]),
         "ecm_b200_stage2_params": (None, [c.c_uint64, u32p, u32p, u32p, u32p]),
         "ecm_b200_fieldop": (c.c_int, [vp, c.c_int, c.c_uint32, u32p, u32p, u32p, c.c_int]),
@@ -90,7 +91,7 @@ EXPORTS = ["ecm_b200_create", "ecm_b200_create_special", "ecm_b200_uses_fold", "
            "ecm_b200_load_curves", "ecm_b200_stage1", "ecm_b200_stage1_ranges", "ecm_b200_stage1_range", "ecm_b200_stage1_begin", "ecm_b200_stage1_step",
            "ecm_b200_stage1_launches", "ecm_b200_sync", "ecm_b200_stage1_progress", "ecm_b200_flush_l2", "ecm_b200_timer", "ecm_b200_read_stage1", "ecm_b200_stage2",
            "ecm_b200_stage2_init", "ecm_b200_stage2_range",
-           "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_stage2_program", "ecm_b200_stage2_pairmap_program", "ecm_b200_pair", "ecm_b200_stage2_params",
+           "ecm_b200_read_stage2", "ecm_b200_stage2_counters", "ecm_b200_plan_stage1", "ecm_b200_plan_stage2", "ecm_b200_stage2_program", "ecm_b200_stage2_pairmap_program", "ecm_b200_rv_program", "ecm_b200_pair", "ecm_b200_stage2_params",
            "ecm_b200_fieldop", "ecm_b200_launch_count", "ecm_b200_last_timing", "ecm_b200_measure_imad_peak"]
 
 
@@ -315,6 +316,13 @@ def stage2_program(b1, b2, which):
     L.ecm_b200_stage2_program(b1, b2, which, buf, n, lay)
     names = ("npb", "pbx", "pbz", "pba", "pax", "paz", "pai", "paa", "qx", "qz", "pdx", "pdz", "entries")
     return list(buf[:n]), dict(zip(names, lay))
+
+
+def rv_program(macro_op):
+    """Phase words of one stage-1 macro-op of the register-resident kernel (rv.cuh)."""
+    buf = (ctypes.c_uint32 * 16)()
+    n = lib().ecm_b200_rv_program(macro_op, buf, 16)
+    return list(buf[:n])
 
 
 def stage2_pairmap_program(b1, amin, pm_v, pm_u):

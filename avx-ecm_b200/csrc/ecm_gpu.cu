@@ -5,6 +5,7 @@
 #include "engine.hpp"
 #include "plan.hpp"
 #include "plan2.hpp"
+#include "rv_prog.hpp"
 #include <cuda_runtime.h>
 #include <atomic>
 #include <thread>
@@ -133,7 +134,8 @@ struct ecm_b200_ctx {
     bool special = false;
     bool fold = false;          // shift-and-fold kernels (special-form base) instead of Montgomery
     uint32_t max_curves = 0, count = 0, groups = 0;
-    uint32_t T = 0, groups_max = 0;   // curves per group (= threads per stage-1 block), groups allocated
+    uint32_t T = 0, groups_max = 0;   // curves per group (one stage-1 block), groups allocated
+    uint32_t threads_s1 = 0;          // threads of a stage-1 block: T * lanes per curve
     Geom G1{0, 0, NSLOT_S1};
     int num_sms = 0;
     cudaStream_t stream = nullptr;
@@ -255,38 +257,48 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
     CUC(eng->prepare());
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&c->ev0)); CUC(cudaEventCreate(&c->ev1));
-    // Curves per group (= threads per stage-1 block).  Whole multiples of 4 warps keep the four SM
+    // Which stage-1 kernel: the register-resident macro-op machine (rv.cuh) where it is compiled for this limb count --
+    // one thread per curve up to 16 limbs, four lanes per curve at 48/64 limbs -- else the slot-file machine (vm.cuh).
+    // The fold kernel set keeps the slot-file machine (it wants more warps than the rv register budget allows).
+    // ECM_B200_S1_KERNEL=vm|rv overrides (A/B measurements, tests that run both).
+    {
+        bool rv = eng->rv_max_threads != 0 && !fold;
+        if (const char *e = getenv("ECM_B200_S1_KERNEL")) {
+            if (!strcmp(e, "vm")) rv = false;
+            else if (!strcmp(e, "rv")) rv = eng->rv_max_threads != 0;
+        }
+        eng->use_rv = rv;
+    }
+    // Curves per group (= one stage-1 block).  Whole multiples of 4 warps keep the four SM
     // sub-partitions evenly loaded (14 warps = 4,4,3,3 measured 6.9 Tprod/s vs 7.2 with 12).  More
     // resident warps hide more latency (throughput ~ w/(w+3.6), measured 12..24 warps), but a batch
     // with fewer groups than SMs leaves SMs idle, while more groups than SMs are time-sliced at full
     // occupancy by the launch schedule.  Pick the block size that maximises the product.
     {
-        const uint32_t S = (uint32_t)eng->stride_s1, sms = (uint32_t)c->num_sms;
+        const uint32_t Lc = eng->use_rv ? (uint32_t)eng->rv_lanes : 1u;        // lanes per curve
+        const uint32_t S = eng->use_rv ? (uint32_t)eng->rv_max_threads : (uint32_t)eng->stride_s1, sms = (uint32_t)c->num_sms;
         // the fold kernels (half the IMADs per product, same loads and carry chains) are bound by dependent-issue
         // latency: measured 67.0k -> 72.8k curves/s from 12 to 16 warps even with 20 of 148 SMs left idle
         const double lat = fold ? 40.0 : 3.6;
         uint32_t bestT = 0; double best = 0;
+        auto consider = [&](uint32_t T) {                 // T = threads per block
+            const uint32_t Tc = T / Lc, gr = (max_curves + Tc - 1) / Tc;
+            const double w = T / 32.0;
+            const double score = (double)std::min(gr, sms) / sms * (w / (w + lat)) * ((double)max_curves / ((double)gr * Tc));
+            if (score > best) { best = score; bestT = T; }
+        };
         // small batches: 1-2 warps per block spread over more SMs finish sooner than a few full blocks
-        for (uint32_t T : {32u, 64u}) {
-            if (T > S) break;
-            const uint32_t gr = (max_curves + T - 1) / T;
-            const double w = T / 32.0;
-            const double score = (double)std::min(gr, sms) / sms * (w / (w + lat)) * ((double)max_curves / ((double)gr * T));
-            if (score > best) { best = score; bestT = T; }
-        }
-        for (uint32_t T = 128; T <= S; T += 128) {
-            const uint32_t gr = (max_curves + T - 1) / T;
-            const double w = T / 32.0;
-            const double score = (double)std::min(gr, sms) / sms * (w / (w + lat)) * ((double)max_curves / ((double)gr * T));
-            if (score > best) { best = score; bestT = T; }
-        }
+        for (uint32_t T : {32u, 64u}) if (T <= S) consider(T);
+        for (uint32_t T = 128; T <= S; T += 128) consider(T);
         if (bestT == 0) bestT = S;                        // kernels whose smem budget allows < 128 threads
         if (const char *e = getenv("ECM_B200_THREADS")) { uint32_t t = (uint32_t)atoi(e); if (t >= 32 && t <= S && t % 32 == 0) bestT = t; }
-        c->T = bestT;
-        c->groups_max = (max_curves + bestT - 1) / bestT;
-        c->G1 = Geom{bestT, (uint32_t)eng->stride_for_threads(bestT), NSLOT_S1};
+        c->threads_s1 = bestT;
+        c->T = bestT / Lc;
+        c->groups_max = (max_curves + c->T - 1) / c->T;
+        const uint32_t stride = eng->use_rv ? (uint32_t)eng->rv_max_threads : (uint32_t)eng->stride_for_threads(bestT);
+        c->G1 = Geom{c->T, stride, NSLOT_S1, Lc};
     }
-    c->state_words = (size_t)c->groups_max * NSLOT_S1 * nl * c->G1.stride;
+    c->state_words = (size_t)c->groups_max * NSLOT_S1 * (nl / c->G1.L) * c->G1.stride;
     CUC(cudaMalloc(&c->d_state, c->state_words * 4));
     CUC(cudaMemsetAsync(c->d_state, 0, c->state_words * 4, c->stream));
     c->d_io_words = (size_t)4 * nl * max_curves + 64;
@@ -473,7 +485,7 @@ int ecm_b200_stage1_step(ecm_b200_ctx *c, uint32_t max_launches, int *done)
     uint32_t n = 0;
     while (c->next_item < c->total_items && n < max_launches) {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(per, c->total_items - c->next_item);
-        c->eng->stage1(c->stream, blocks, c->T, c->d_state, c->d_ops + c->seg_begin, c->seg_len, c->chunk_len, c->groups, c->next_item);
+        c->eng->stage1(c->stream, blocks, c->threads_s1, c->d_state, c->d_ops + c->seg_begin, c->seg_len, c->chunk_len, c->groups, c->next_item);
         c->next_item += blocks; c->launches_issued++; c->last_launches++; n++;
     }
     CU(cudaGetLastError());
@@ -956,6 +968,16 @@ uint64_t ecm_b200_stage2_pairmap_program(uint64_t b1, uint32_t amin, const uint3
     const std::vector<uint64_t> &src = pg.ranges.back();
     if (out && cap >= src.size()) memcpy(out, src.data(), src.size() * 8);
     return src.size();
+}
+
+int ecm_b200_rv_program(int macro_op, uint32_t *phases, int cap)
+{
+    static const uint32_t prog[8][RV_MAXPROG] = { RV_PROGRAMS };
+    if (macro_op < 0 || macro_op > 7 || !phases) return 0;
+    int n = 0;
+    while ((prog[macro_op][n] & 15u) != PH_END) n++;
+    for (int k = 0; k < n && k < cap; k++) phases[k] = prog[macro_op][k];
+    return n;
 }
 
 void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R)

@@ -12,6 +12,10 @@ typedef std::vector<uint32_t> Big;
 
 struct Engine {
     int nl = 0, stride_s1 = 0, smem_s1 = 0;      // stride_s1 = max threads per stage-1 block
+    // Register-resident macro-op machine (rv.cuh).  rv_lanes = lanes per curve of that stage-1 kernel (> 1: the
+    // warp-cooperative layout); rv_max_threads = largest block the rv kernel serves (0: not compiled for this limb count).
+    int rv_lanes = 1, rv_max_threads = 0;
+    bool use_rv = false;                          // set by the context before prepare()
     // lane stride of the stage-1 state for blocks of T threads (the stage-1 kernel instance serving T fixes it)
     virtual int stride_for_threads(uint32_t T) const = 0;
     size_t params_bytes = 0;

@@ -1,13 +1,27 @@
 // engine_inst.cu -- instantiates every kernel for ONE limb count (compile with -DECM_NL=<n>).
 #include "engine.hpp"
 #include "kernels.cuh"
+#include "rv.cuh"
 
 #ifndef ECM_NL
 #error "compile with -DECM_NL=<limbs>"
 #endif
 
+#include <type_traits>
 namespace ecmb200 {
 inline namespace ECM_VNS {
+
+// which field policy the register-resident stage-1 machine (rv.cuh) uses for a limb count, if any: one thread per curve
+// up to 16 limbs (four operand values + two accumulator pairs fit the registers of a 384-thread block), four lanes per
+// curve at 48 and 64 limbs (coop.cuh).  20-32 limbs keep the slot-file machine (dedicated squaring, 0.92 of the roof).
+template <int NL, class Enable = void> struct RvCfg { static constexpr int MAXT = 0; typedef void Field; };
+template <int NL> struct RvCfg<NL, typename std::enable_if<(NL <= 16)>::type> { static constexpr int MAXT = 384; typedef SoloField<NL> Field; };
+#if !ECM_SPECIAL
+template <> struct RvCfg<48> { static constexpr int MAXT = 384; typedef CoopField<12, 4> Field; };
+template <> struct RvCfg<64> { static constexpr int MAXT = 384; typedef CoopField<16, 4> Field; };
+#endif
+template <class F> struct RvLanes { static constexpr int L = F::L, M = F::M; };
+template <> struct RvLanes<void> { static constexpr int L = 1, M = 1; };
 
 template <int NL>
 struct EngineT : Engine {
@@ -18,6 +32,7 @@ struct EngineT : Engine {
         nl = NL; stride_s1 = S1Cfg<NL>::STRIDE; smem_s1 = S1Cfg<NL>::smem;
         params_bytes = sizeof(ModParams<NL>);
         threads_s2 = S2Cfg<NL>::THREADS; smem_s2 = S2Cfg<NL>::smem; nslot_s2 = NSLOT_S2;
+        rv_max_threads = RvCfg<NL>::MAXT; rv_lanes = RvLanes<typename RvCfg<NL>::Field>::L;
     }
     void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, const Big &rref, uint32_t m0inv) override
     {
@@ -39,6 +54,11 @@ struct EngineT : Engine {
         if constexpr (S1Small<NL>::MAXT != S1Cfg<NL>::STRIDE) {
             e = cudaFuncSetAttribute(k_stage1<NL, S1Small<NL>::MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      S1Cfg<NL>::per_thread * S1Small<NL>::MAXT);
+            if (e != cudaSuccess) return e;
+        }
+        if constexpr (RvCfg<NL>::MAXT != 0) {
+            typedef typename RvCfg<NL>::Field F;
+            e = cudaFuncSetAttribute(k_stage1_rv<F, RvCfg<NL>::MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * F::M * 4 * RvCfg<NL>::MAXT);
             if (e != cudaSuccess) return e;
         }
         threads_pair = PairCfg<NL>::THREADS;
@@ -80,6 +100,14 @@ struct EngineT : Engine {
     void stage1(cudaStream_t st, uint32_t blocks, uint32_t threads, uint32_t *state, const uint8_t *ops, uint64_t nops,
                 uint32_t chunk_len, uint32_t groups, uint64_t item0) override
     {
+        if constexpr (RvCfg<NL>::MAXT != 0) {
+            if (use_rv) {
+                typedef typename RvCfg<NL>::Field F;
+                k_stage1_rv<F, RvCfg<NL>::MAXT><<<blocks, threads, 2 * F::M * 4 * RvCfg<NL>::MAXT, st>>>(P, state, ops, nops, chunk_len, groups, item0);
+                count_launch();
+                return;
+            }
+        }
         if (S1Small<NL>::MAXT != S1Cfg<NL>::STRIDE && threads <= (uint32_t)S1Small<NL>::MAXT)
             k_stage1<NL, S1Small<NL>::MAXT><<<blocks, threads, S1Cfg<NL>::per_thread * S1Small<NL>::MAXT, st>>>(P, state, ops, nops, chunk_len, groups, item0);
         else

@@ -143,6 +143,10 @@ uint64_t ecm_b200_stage2_program(uint64_t b1, uint64_t b2, int which, uint64_t *
  * 0 when the pairmap is rejected (it would leave the tables).  For CPU-side checking, no GPU needed.      */
 uint64_t ecm_b200_stage2_pairmap_program(uint64_t b1, uint32_t amin, const uint32_t *pm_v, const uint32_t *pm_u, uint32_t steps,
                                          uint64_t *out, uint64_t cap);
+/* Phase program of one stage-1 macro-op (0 DBL, 1 INIT, 2..5 PRAC rules 3/4/5/9, 6 FINAL) of the register-resident
+ * stage-1 kernel: phase word = kind | x<<4 | y<<8 | z<<12 | flag<<16 with kind 0 A1, 1 A2, 2 A3, 3 D1L, 4 D1P, 5 D2,
+ * 6 D3, 7 COPY (avx-ecm_b200/csrc/rv_prog.hpp, rv.cuh).  Returns the number of phases.  For CPU-side checking.     */
+int ecm_b200_rv_program(int macro_op, uint32_t *phases, int cap);
 /* Stage-2 geometry chosen for B1 (thread_init, main.c:834-970): D, U, L, R.                    */
 void ecm_b200_stage2_params(uint64_t b1, uint32_t *D, uint32_t *U, uint32_t *L, uint32_t *R);
 

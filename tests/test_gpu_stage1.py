@@ -257,3 +257,53 @@ def test_gpu_lines_are_valid_gmp_ecm_resume_points():
     base = (1 << 277) - 1
     r = E.vececm(base, 12, 5000, b2=5000, sigma=rng.randrange(6, 2 ** 63), base=base)
     assert [check_line(l, expect_n=base, base=base) for l in r["save_lines"]] == ["ok"] * 12
+
+
+@pytest.mark.parametrize("name,curves,b1", [("small96", 70, 3000), ("syn206", 70, 3000), ("t35", 200, 3000), ("syn415", 500, 5000),
+                                            ("readme508", 200, 3000), ("slow_csh_line07", 100, 1500), ("syn2048", 150, 1000)])
+def test_register_machine_and_slot_machine_kernels_agree(name, curves, b1, monkeypatch):
+    """Stage 1 has two kernel generations: the slot-file machine (vm.cuh, one thread per curve) and the register-resident
+    macro-op machine (rv.cuh) -- one thread per curve up to 16 limbs, FOUR LANES per curve (warp-cooperative limbs,
+    coop.cuh) at 48 and 64 limbs.  Same op stream, different state layouts and arithmetic routines: every residue of every
+    curve must be identical, and equal to the oracle's (3, 7, 10, 13, 16, 48 and 64 limbs)."""
+    N = composites()[name] if name in composites() else int(GOLDEN[name]["n"])
+    sig = [1000 + 3 * i for i in range(curves)]
+    res = {}
+    for kern in ("vm", "rv"):
+        monkeypatch.setenv("ECM_B200_S1_KERNEL", kern)
+        ctx = E.EcmContext(N, curves)
+        try:
+            ctx.build_curves(sig); ctx.stage1(b1)
+            res[kern] = ctx.read_stage1()
+        finally:
+            ctx.close()
+    assert res["vm"] == res["rv"]
+    for i in (0, curves // 3, curves - 1):
+        o = O.ecm_curve(N, b1, b1, sig[i])
+        assert (res["rv"][0][i], res["rv"][1][i]) == (o["x"], o["z"])
+
+
+def test_cooperative_kernel_with_ragged_batches_and_stage2(monkeypatch):
+    """2048-bit curves on the four-lanes-per-curve kernel: batch sizes that do not fill a warp's eight curves or a block,
+    time-sliced launches, and stage 2 (one thread per curve) picking the points up from the cooperative layout."""
+    N = composites()["syn2048"]
+    for count in (1, 7, 9, 97, 200):
+        sig = [50 + i for i in range(count)]
+        ctx = E.EcmContext(N, count)
+        try:
+            ctx.build_curves(sig); ctx.stage1_begin(700)
+            while not ctx.stage1_step(1):
+                pass
+            ctx.sync()
+            x, z, _ = ctx.read_stage1()
+            acc = None
+            if count == 9:
+                ctx.stage2(700, 30000)
+                acc = ctx.read_stage2()[0]
+        finally:
+            ctx.close()
+        for i in {0, count // 2, count - 1}:
+            o = O.ecm_curve(N, 700, 30000 if acc else 700, sig[i])
+            assert (x[i], z[i]) == (o["x"], o["z"]), (count, i)
+            if acc:
+                assert acc[i] == o["acc"]

@@ -56,6 +56,65 @@ def test_stage1_stream_reproduces_oracle_residues(name, b1, sigma):
     assert (X, Z) == (o["x"], o["z"])
 
 
+def run_stage1_phases(N, x, s, ops):
+    """Interpret the PHASE programs of the register-resident stage-1 kernel (rv.cuh) exactly as k_stage1_rv does: four
+    operand registers A0, A1, B0, B1, a two-value park, point slots addressed through the macro-op's permutation."""
+    progs = [E.rv_program(t) for t in range(8)]
+    pts = {0: [x, 1], 1: [0, 0], 2: [0, 0], 3: [0, 0]}
+    A0 = A1 = B0 = B1 = 0
+    park = [0, 0]
+    last_T = 0
+    for b in ops:
+        t, p = b & 7, PERM[b >> 3]
+        phys = lambda sym: (p >> (2 * sym)) & 3
+        for u in progs[t]:
+            kind, px, py, flag = u & 15, phys((u >> 4) & 3), phys((u >> 8) & 3), (u >> 16) & 1
+            if kind == 0:                                      # A1
+                X, Z = pts[px]; A0, A1 = (X - Z) % N, (X + Z) % N
+                X, Z = pts[py]; B0, B1 = (X + Z) % N, (X - Z) % N
+                if flag:
+                    park = [B0, B1]
+            elif kind == 1:                                    # A2
+                A0, A1 = (A0 + A1) % N, (A0 - A1) % N
+                B0, B1 = A0, A1
+            elif kind == 2:                                    # A3
+                B0, B1 = pts[px][1], pts[px][0]
+            elif kind in (3, 4):                               # D1L / D1P
+                if kind == 3:
+                    X, Z = pts[px]; A0, A1 = (X + Z) % N, (X - Z) % N
+                else:
+                    A0, A1 = park
+                B0, B1 = A0, A1
+            elif kind == 5:                                    # D2
+                B0, B1, A1 = A1, (A0 - A1) % N, s
+            elif kind == 6:                                    # D3
+                pts[px][0] = A0
+                A0 = (A1 + B0) % N
+            elif kind == 7:                                    # COPY
+                pts[py] = list(pts[px])
+                continue
+            if kind == 6:
+                A0 = A0 * B1 % N
+                pts[px][1] = A0
+            else:
+                A0, A1 = A0 * B0 % N, A1 * B1 % N
+                if kind == 2:
+                    pts[py] = [A0, A1]
+        if t in (0, 6):
+            last_T = (p >> 6) & 3
+    return tuple(pts[last_T])
+
+
+@pytest.mark.parametrize("name,b1,sigma", [("syn415", 3000, 7), ("t35", 1200, 2 ** 63 + 5), ("syn2048", 300, 12)])
+def test_rv_phase_programs_reproduce_oracle_residues(name, b1, sigma):
+    N = composites()[name]
+    x, s = O.build_curve(N, sigma)
+    ops, _, _ = E.plan_stage1(b1)
+    X, Z = run_stage1_phases(N, x, s, ops)
+    o = O.ecm_curve(N, b1, b1, sigma)
+    assert (X, Z) == (o["x"], o["z"])
+
+
 def run_stage2_program(N, code, slots, tab):
     UX, ACC, S1, SP, T1 = 0, 6, 7, 11, 12
     for ins in code:

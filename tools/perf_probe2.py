@@ -6,7 +6,8 @@ sys.path.insert(0, ROOT)
 import avx_ecm_b200 as E
 
 name, curves, b1, b2 = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-N = int(json.load(open(os.path.join(ROOT, "tests/golden/composites.json")))[name])
+comp = json.load(open(os.path.join(ROOT, "tests/golden/composites.json")))
+N = int(comp[name]) if name in comp else int(json.load(open(os.path.join(ROOT, "tests/golden", name + ".json")))["n"])
 ctx = E.EcmContext(N, curves)
 nl = ctx.nl
 W = 2 * nl * nl + nl
