@@ -268,6 +268,9 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
             else if (!strcmp(e, "rv")) rv = eng->rv_max_threads != 0;
         }
         eng->use_rv = rv;
+        bool cs2 = eng->has_coop_s2;                      // stage 2 on the four-lanes-per-curve layout (coop_s2.cuh)
+        if (const char *e = getenv("ECM_B200_S2_KERNEL")) { if (!strcmp(e, "solo")) cs2 = false; }
+        eng->use_coop_s2 = cs2;
     }
     // Curves per group (= one stage-1 block).  Whole multiples of 4 warps keep the four SM
     // sub-partitions evenly loaded (14 warps = 4,4,3,3 measured 6.9 Tprod/s vs 7.2 with 12).  More

@@ -16,6 +16,8 @@ struct Engine {
     // warp-cooperative layout); rv_max_threads = largest block the rv kernel serves (0: not compiled for this limb count).
     int rv_lanes = 1, rv_max_threads = 0;
     bool use_rv = false;                          // set by the context before prepare()
+    // stage 2 on the cooperative layout (coop_s2.cuh): compiled for this limb count / selected (before prepare())
+    bool has_coop_s2 = false, use_coop_s2 = false;
     // lane stride of the stage-1 state for blocks of T threads (the stage-1 kernel instance serving T fixes it)
     virtual int stride_for_threads(uint32_t T) const = 0;
     size_t params_bytes = 0;
@@ -34,10 +36,10 @@ struct Engine {
     virtual void read_point(cudaStream_t st, const uint32_t *state, Geom G, uint32_t count, uint32_t xs, uint32_t zs,
                             uint32_t *x, uint32_t *z, uint8_t *flag, uint32_t *g, const uint32_t *chk) = 0;
     // stage 2
-    int threads_s2 = 0, smem_s2 = 0, nslot_s2 = 0;
+    int threads_s2 = 0, smem_s2 = 0, nslot_s2 = 0;       // threads_s2 = CURVES per group of the state2 layout
     virtual void vm2(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, uint32_t *tab, const uint64_t *code,
                      uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0, uint8_t *inv_fail) = 0;
-    int threads_pair = 0, pair_blocks_per_sm = 1;
+    int threads_pair = 0, pair_blocks_per_sm = 1;        // threads_pair = CURVES per block of the pair kernel
     bool use_pair_kernel = true;                  // false for wide moduli: the pair steps run inside k_vm2
     virtual void pair_run(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, const uint32_t *tab, const uint64_t *code,
                           uint32_t npairs, uint32_t ncurves, uint32_t chunk_len, uint32_t groups, uint64_t item0) = 0;

@@ -2,6 +2,7 @@
 #include "engine.hpp"
 #include "kernels.cuh"
 #include "rv.cuh"
+#include "coop_s2.cuh"
 
 #ifndef ECM_NL
 #error "compile with -DECM_NL=<limbs>"
@@ -20,6 +21,12 @@ template <int NL> struct RvCfg<NL, typename std::enable_if<(NL <= 16)>::type> { 
 template <> struct RvCfg<48> { static constexpr int MAXT = 384; typedef CoopField<12, 4> Field; };
 template <> struct RvCfg<64> { static constexpr int MAXT = 384; typedef CoopField<16, 4> Field; };
 #endif
+// stage 2 on the cooperative layout (coop_s2.cuh) where stage 1 has it
+template <int NL> struct S2CoopCfg { static constexpr int M = 0, L = 1; };
+#if !ECM_SPECIAL
+template <> struct S2CoopCfg<48> { static constexpr int M = 12, L = 4; };
+template <> struct S2CoopCfg<64> { static constexpr int M = 16, L = 4; };
+#endif
 template <class F> struct RvLanes { static constexpr int L = F::L, M = F::M; };
 template <> struct RvLanes<void> { static constexpr int L = 1, M = 1; };
 
@@ -33,6 +40,7 @@ struct EngineT : Engine {
         params_bytes = sizeof(ModParams<NL>);
         threads_s2 = S2Cfg<NL>::THREADS; smem_s2 = S2Cfg<NL>::smem; nslot_s2 = NSLOT_S2;
         rv_max_threads = RvCfg<NL>::MAXT; rv_lanes = RvLanes<typename RvCfg<NL>::Field>::L;
+        has_coop_s2 = S2CoopCfg<NL>::M != 0;
     }
     void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, const Big &rref, uint32_t m0inv) override
     {
@@ -61,6 +69,18 @@ struct EngineT : Engine {
             e = cudaFuncSetAttribute(k_stage1_rv<F, RvCfg<NL>::MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * F::M * 4 * RvCfg<NL>::MAXT);
             if (e != cudaSuccess) return e;
         }
+        if constexpr (S2CoopCfg<NL>::M != 0) {
+            if (use_coop_s2) {
+                typedef CoopS2Cfg<S2CoopCfg<NL>::M, S2CoopCfg<NL>::L> C;
+                threads_s2 = C::CURVES; smem_s2 = C::smem;
+                threads_pair = C::PAIR_THREADS / S2CoopCfg<NL>::L;
+                use_pair_kernel = true;
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pair_blocks_per_sm, k_pair_coop<S2CoopCfg<NL>::M, S2CoopCfg<NL>::L>, C::PAIR_THREADS, 0);
+                if (e != cudaSuccess) return e;
+                if (pair_blocks_per_sm < 1) pair_blocks_per_sm = 1;
+                return cudaFuncSetAttribute(k_vm2_coop<S2CoopCfg<NL>::M, S2CoopCfg<NL>::L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
+            }
+        }
         threads_pair = PairCfg<NL>::THREADS;
         use_pair_kernel = (NL <= 32);
         if (!use_pair_kernel) return cudaFuncSetAttribute(k_vm2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
@@ -72,12 +92,30 @@ struct EngineT : Engine {
     void vm2(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, uint32_t *tab, const uint64_t *code,
              uint64_t ncode, uint32_t chunk_len, uint32_t groups, uint64_t item0, uint8_t *inv_fail) override
     {
+        if constexpr (S2CoopCfg<NL>::M != 0) {
+            if (use_coop_s2) {
+                constexpr int M = S2CoopCfg<NL>::M, L = S2CoopCfg<NL>::L;
+                k_vm2_coop<M, L><<<blocks, CoopS2Cfg<M, L>::THREADS, smem_s2, st>>>(P, Pg, state2, cap, tab, code, ncode, chunk_len, groups, item0, inv_fail);
+                count_launch();
+                return;
+            }
+        }
         k_vm2<NL><<<blocks, threads_s2, smem_s2, st>>>(P, Pg, state2, cap, tab, code, ncode, chunk_len, groups, item0, inv_fail);
         count_launch();
     }
     void pair_run(cudaStream_t st, uint32_t blocks, uint32_t *state2, uint32_t cap, const uint32_t *tab, const uint64_t *code,
                   uint32_t npairs, uint32_t ncurves, uint32_t chunk_len, uint32_t groups, uint64_t item0) override
     {
+        if constexpr (S2CoopCfg<NL>::M != 0) {
+            if (use_coop_s2) {
+                constexpr int M = S2CoopCfg<NL>::M, L = S2CoopCfg<NL>::L;
+                uint32_t nlanes = (ncurves * L + 31) / 32 * 32;
+                if (nlanes > cap * L) nlanes = cap * L;
+                k_pair_coop<M, L><<<blocks, CoopS2Cfg<M, L>::PAIR_THREADS, 0, st>>>(P, state2, cap, tab, code, npairs, nlanes, chunk_len, groups, item0);
+                count_launch();
+                return;
+            }
+        }
         if constexpr (NL <= 32) {
             k_pair<NL><<<blocks, PairCfg<NL>::THREADS, 0, st>>>(P, state2, cap, tab, code, npairs, ncurves, chunk_len, groups, item0);
             count_launch();
@@ -87,12 +125,26 @@ struct EngineT : Engine {
                   uint32_t first, uint32_t count, uint32_t *state2, uint32_t cap2, uint32_t *tab, uint32_t e_qx, uint32_t e_qz,
                   uint8_t *inv_fail) override
     {
+        if constexpr (S2CoopCfg<NL>::M != 0) {
+            if (use_coop_s2) {
+                k_s2_setup_coop<S2CoopCfg<NL>::M, S2CoopCfg<NL>::L><<<(cap2 + 127) / 128, 128, 0, st>>>(state1, dg(G1), xslot, zslot, spslot, first, count, state2, cap2, tab, e_qx, e_qz, inv_fail);
+                count_launch();
+                return;
+            }
+        }
         k_s2_setup<NL><<<(cap2 + 127) / 128, 128, 0, st>>>(state1, dg(G1), xslot, zslot, spslot, first, count, state2, cap2, tab, e_qx, e_qz, inv_fail);
         count_launch();
     }
     void s2_collect(cudaStream_t st, const uint32_t *state2, uint32_t cap2, const uint8_t *inv_fail, uint32_t first, uint32_t n,
                     uint32_t count, uint32_t *acc_out, uint8_t *fail_out) override
     {
+        if constexpr (S2CoopCfg<NL>::M != 0) {
+            if (use_coop_s2) {
+                k_s2_collect_coop<S2CoopCfg<NL>::M, S2CoopCfg<NL>::L><<<(n + 127) / 128, 128, 0, st>>>(state2, cap2, inv_fail, first, n, count, acc_out, fail_out);
+                count_launch();
+                return;
+            }
+        }
         k_s2_collect<NL><<<(n + 127) / 128, 128, 0, st>>>(state2, cap2, inv_fail, first, n, count, acc_out, fail_out);
         count_launch();
     }

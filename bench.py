@@ -19,7 +19,16 @@ curves x (fraction of the job's field operations executed) / time.
   roofline  algorithmic 32x32->64 products/s (modmuls x (2n^2+n)) against the IMAD.WIDE issue peak
             measured live on the same GPU (ecm_b200_measure_imad_peak)
   cpu_baseline / --impl reference   the unmodified reference (oracle/_ref/avx-ecm-ref, SKYLAKEX build)
-            on all host threads
+            on all host threads, at the same B1 = 1e6 whenever the samples fit the time budget
+
+`also` carries bounded samples of the other BASELINE configs, each with an oracle check and a roofline that counts
+EVERY modular product of the compiled programs:
+  config2_1024bit   [2] 1024-bit, B1 = 3e6: launches of the stage-1 schedule at 65 536 curves; stage 2 (B2 = 3e8
+                    geometry) = ecm_stage2_init + the first pairmap steps of the first prime range on one wave
+  config4_2048bit   [4] 2048-bit, B1 = 1.1e7: the same on the four-lanes-per-curve kernels
+  sweep             [4]'s partitioning: ONE sigma range split over the ranks (strong scaling, avx_ecm_b200.dist.run_sharded),
+                    merged on rank 0 in sigma order; `merged_sha256` must be the same at every N
+Full-size runs of the other configs:  --config syn1024_s12 | syn2048_sweep  (minutes to hours; results under profiles/).
 """
 import argparse
 import json
@@ -42,6 +51,19 @@ COMPOSITE = "syn415"
 S1_ADDS, S1_DUPS = 1980817, 217929                  # ecm.c:1849 printout for B1=1e6
 MODMUL_PER_CURVE = 6 * S1_ADDS + 5 * S1_DUPS        # 12 974 547
 METRIC = "stage1_curves_per_sec_B1_1e6_415bit"
+
+
+PROFILE_SUMMARY = "profiles/r2_final_stage1_ncu_full_summary.txt"
+
+
+def profile_traffic():
+    try:
+        txt = open(os.path.join(ROOT, PROFILE_SUMMARY)).read()
+        rd = float(re.search(r"dram__bytes_read.sum \[Mbyte\] = ([0-9.]+)", txt).group(1))
+        wr = float(re.search(r"dram__bytes_write.sum \[Mbyte\] = ([0-9.]+)", txt).group(1))
+        return int((rd + wr) * 1e6)
+    except Exception:
+        return None
 
 
 def composite():
@@ -136,8 +158,13 @@ def reference_arm(args, rank):
     threads = host_threads()
     steps = args.steps if args.steps else 3
     warm = args.warmup if args.warmup is not None else 1
-    b1s = B1 if (steps + warm) * 8.0 <= 180 else 100000
-    for _ in range(warm):
+    # same config as the GPU arm (B1 = 1e6) whenever steps + warm-up samples fit ~4 minutes; the first sample is
+    # timed to decide (it is a warm-up sample if any were asked for, else an extra one)
+    t0 = time.time()
+    first = run_reference_sample(B1, threads)
+    t_full = time.time() - t0
+    b1s = B1 if (steps + max(warm - 1, 0)) * t_full <= 240 else 100000
+    for _ in range(max(warm - 1, 0)):
         run_reference_sample(b1s, threads)
     t0 = time.time()
     rates = []
@@ -151,7 +178,8 @@ def reference_arm(args, rank):
         "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u52-in-f64/u64 (AVX-512)",
         "data": "synthetic",
         "config": {"workload": "synthetic 415-bit composite, B1=1e6, stage 1 only, sigma=7.. (each step = one bounded sample)",
-                   "composite": COMPOSITE, "b1": B1, "sample_b1": b1s},
+                   "composite": COMPOSITE, "b1": B1, "sample_b1": b1s, "same_config": b1s == B1,
+                   "first_full_b1_sample": {"curves_per_sec": first[0], "seconds": t_full}},
         "cpu_baseline": {"value": v, "unit": "curves/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": v, "unit": "curves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -162,6 +190,263 @@ def reference_arm(args, rank):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# bounded samples of the other BASELINE configs (`also`) and the strong-scaling sweep sample
+# ------------------------------------------------------------------------------------------------
+def named_composite(name):
+    return int(json.load(open(os.path.join(ROOT, "tests", "golden", "composites.json")))[name])
+
+
+def program_modmuls(words):
+    """Modular products (and inversions) in a compiled stage-2 program: V_MUL/V_SQR/V_PAIR = 1, V_MUL2 = 2 (plan2.hpp)."""
+    mm = inv = pairs = 0
+    for w in words:
+        op = w & 0xff
+        if op in (0, 1):
+            mm += 1
+        elif op == 10:
+            mm += 1
+            pairs += 1
+        elif op == 12:
+            mm += 2
+        elif op == 8:
+            inv += 1
+    return mm, inv, pairs
+
+
+def oracle_check(E, ctx, N, sig, b1, b2, picks):
+    """Coherent small run on the SAME context (same kernels, batch geometry and layouts as the timed sample): stage 1 to
+    b1, stage 2 to b2, curves `picks` compared with the oracle (test infrastructure; outside every timed region)."""
+    import oracle_lib as O
+    ctx.build_curves(sig)
+    ctx.stage1(b1)
+    x, z, _ = ctx.read_stage1()
+    acc = None
+    if b2 > b1:
+        ctx.stage2(b1, b2)
+        acc = ctx.read_stage2()[0]
+    ok = True
+    for i in picks:
+        o = O.ecm_curve(N, b1, b2, sig[i])
+        ok = ok and (x[i], z[i]) == (o["x"], o["z"]) and (acc is None or acc[i] == o["acc"])
+    return bool(ok)
+
+
+def config_sample(E, name, b1, curves_s1, curves_s2, launches, span, peak_prod, device, chk):
+    """BASELINE config [2] / [4] as a bounded sample on one GPU.  Stage 1: `launches` launches of the schedule for b1
+    on curves_s1 curves.  Stage 2 with the geometry of b1 (B2 = 100 b1): ecm_b200_stage2_init, then ecm_b200_stage2_range
+    over the primes of [b1, b1 + span) -- the head of the first prime range -- on curves_s2 curves (one wave).
+    chk = (b1, b2) of the coherent small run that is compared with the oracle on the same contexts."""
+    N = named_composite(name)
+    out = {"composite": name, "b1": b1, "b2": 100 * b1}
+    _, adds, dups = E.plan_stage1(b1)
+    modmul1 = 6 * adds + 5 * dups
+    sig = [SIGMA0 + i for i in range(curves_s1)]
+    ctx = E.EcmContext(N, curves_s1, device=device)
+    try:
+        nl = ctx.nl
+        W = 2 * nl * nl + nl
+        ctx.build_curves(sig); ctx.stage1_begin(b1)
+        total, _ = ctx.stage1_launches()
+        ctx.stage1_step(1); ctx.sync()
+        ctx.build_curves(sig); ctx.stage1_begin(b1)
+        ctx.timer_start(); ctx.stage1_step(launches); frac = ctx.stage1_progress(); ctx.timer_stop(); ctx.sync()
+        ms = ctx.timer_ms()
+        rate = curves_s1 * frac / (ms / 1e3)
+        out["stage1"] = {"curves": curves_s1, "limbs": nl, "launches_timed": launches, "launches_per_full_job": total,
+                         "ms_per_launch": ms / launches, "curves_per_sec": rate, "point_adds": adds, "point_doubles": dups,
+                         "modmul_per_curve": modmul1, "products_per_sec": rate * modmul1 * W,
+                         "frac_of_imad_peak": rate * modmul1 * W / peak_prod,
+                         "residue_check_vs_oracle": oracle_check(E, ctx, N, sig, chk[0], chk[0], (0, curves_s1 - 1)),
+                         "residue_check": "full stage 1 at B1=%d on this context, first and last curve" % chk[0]}
+    finally:
+        ctx.close()
+    # stage 2
+    D, U, L, R = E.stage2_params(b1)
+    sig = [SIGMA0 + i for i in range(curves_s2)]
+    ctx = E.EcmContext(N, curves_s2, device=device)
+    try:
+        ok = oracle_check(E, ctx, N, sig, chk[0], chk[1], (0, curves_s2 - 1))
+        init_words, lay = E.stage2_program(b1, 100 * b1, -1)
+        mm_init, inv_init, _ = program_modmuls(init_words)
+        pm_v, pm_u, _, npairs = E.pair(b1, b1 + span, D)
+        amin = (b1 + D) // (2 * D)
+        mm_rng, inv_rng, pairs = program_modmuls(E.stage2_pairmap_program(b1, amin, pm_v, pm_u))
+        ctx.build_curves(sig); ctx.stage1(chk[0])           # any point serves as Q
+        t0 = time.time()
+        ctx.stage2_init(b1)
+        ms_init, l_init = ctx.last_timing()
+        ctx.stage2_range(amin, pm_v, pm_u)
+        ms_rng, l_rng = ctx.last_timing()
+        wall = time.time() - t0
+        acc = ctx.read_stage2()[0]
+        out["stage2"] = {
+            "curves": curves_s2, "D": D, "table_entries_per_curve": lay["entries"], "table_bytes": lay["entries"] * 4 * nl * curves_s2,
+            "init": {"device_s": ms_init / 1e3, "launches": l_init, "modmul_per_curve": mm_init, "inversions_per_curve": inv_init,
+                     "products_per_sec": curves_s2 * mm_init * W / (ms_init / 1e3), "frac_of_imad_peak": curves_s2 * mm_init * W / (ms_init / 1e3) / peak_prod},
+            "range_head": {"primes": [b1, b1 + span], "pairmap_steps": len(pm_v), "pairs": npairs, "device_s": ms_rng / 1e3, "launches": l_rng,
+                           "modmul_per_curve": mm_rng, "pair_products_per_curve": pairs, "inversions_per_curve": inv_rng,
+                           "products_per_sec": curves_s2 * mm_rng * W / (ms_rng / 1e3),
+                           "frac_of_imad_peak": curves_s2 * mm_rng * W / (ms_rng / 1e3) / peak_prod,
+                           "table_read_GBs_algorithmic": 2 * pairs * 4 * nl * curves_s2 / (ms_rng / 1e3) / 1e9, "hbm_peak_GBs": 6540.8},
+            "wall_s": wall, "accumulators_nontrivial": bool(len(set(acc[:64])) > 1),
+            "note": "every modular product of the compiled programs is counted (products x (2n^2+n)); inversions are extra work, not counted",
+            "check_vs_oracle": ok, "check": "stage 1 to %d + stage 2 to %d on this context, first and last curve" % chk}
+    finally:
+        ctx.close()
+    return out
+
+
+def sweep_sample(E, torch, dist, rank, world, device, total_curves, b1):
+    """BASELINE config [4]'s partitioning as a bounded sample: ONE sigma range of total_curves 2048-bit curves split over the
+    ranks (strong scaling), stage 1 at b1, save lines gathered on rank 0 in sigma order.  Returns the dict on rank 0."""
+    import hashlib
+    from avx_ecm_b200 import dist as D
+    N = named_composite("syn2048")
+    first, count = D.shard_range(total_curves, rank, world)
+    ctx = E.EcmContext(N, max(count, 1), device=device)
+    dev_ms = [0.0]
+
+    def compute(first_sigma, cnt):
+        r = E.vececm(N, cnt, b1, b2=b1, sigma=first_sigma, ctx=ctx)
+        dev_ms[0] = ctx.last_timing()[0]
+        return r
+    try:
+        E.plan_stage1(b1)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        merged = D.run_sharded(total_curves, SIGMA0, compute)
+        if dist:
+            dist.barrier()
+        wall = time.time() - t0
+    finally:
+        ctx.close()
+    wall = D.all_max(wall) if dist else wall
+    dev = (D.all_max(dev_ms[0]) if dist else dev_ms[0]) / 1e3
+    if rank != 0:
+        return None
+    import oracle_lib as O
+    ok = all(merged["save_lines"][i] == O.ecm_curve(N, b1, b1, merged["sigmas"][i])["save_line"] for i in (0, total_curves - 1))
+    _, adds, dups = E.plan_stage1(b1)
+    return {"workload": "2048-bit, %d curves in ONE sigma range split over %d GPU(s), stage 1 at B1=%d, lines merged in sigma order" % (total_curves, world, b1),
+            "scaling": "strong", "curves_total": total_curves, "n_gpus": world, "b1": b1,
+            "stage1_device_s_max_over_ranks": dev, "wall_s_with_gather": wall,
+            "curves_per_sec": total_curves / dev, "curves_per_sec_wall": total_curves / wall,
+            "products_per_sec": total_curves / dev * (6 * adds + 5 * dups) * (2 * 64 * 64 + 64),
+            "merged_lines": len(merged["save_lines"]), "merged_sha256": hashlib.sha256("".join(merged["save_lines"]).encode()).hexdigest(),
+            "first_and_last_line_vs_oracle": bool(ok)}
+
+
+def cli_multi_gpu_check(world):
+    """The product's own multi-GPU path: avx-ecm-b200 with <world> GPUs (one host thread per GPU) on a golden case must
+    write the reference's save_b1.txt byte for byte."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "syn415_b1_3e4_s1only.json")))
+    cli = os.path.join(ROOT, "avx-ecm_b200", "avx-ecm-b200")
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([cli, g["n"], str(len(g["save_lines"])), str(g["b1"]), str(world), str(g["b2"]), g["sigma0"]],
+                           cwd=d, capture_output=True, text=True)
+        if r.returncode != 0:
+            return {"error": (r.stdout + r.stderr)[-300:]}
+        return {"case": "syn415_b1_3e4_s1only", "gpus": world, "identical": open(os.path.join(d, "save_b1.txt")).read() == "".join(g["save_lines"])}
+
+
+def s2_program_modmuls(E, b1, b2):
+    """(modular products, inversions, pair products) per curve of the whole compiled stage-2 program for (b1, b2)."""
+    mm, inv, pairs = program_modmuls(E.stage2_program(b1, b2, -1)[0])
+    which = 0
+    while b1 + which * 100000000 < b2:
+        a, b, c = program_modmuls(E.stage2_program(b1, b2, which)[0])
+        mm, inv, pairs, which = mm + a, inv + b, pairs + c, which + 1
+    return mm, inv, pairs
+
+
+def full_config_run(args, E, torch, dist, rank, world, device):
+    """--config syn1024_s12 / syn2048_sweep: a BASELINE config at full size (or with --b1 / --curves overrides), both stages,
+    one sigma range split over the ranks, merged on rank 0.  One JSON line."""
+    import hashlib
+    from avx_ecm_b200 import dist as D
+    if args.config == "syn1024_s12":
+        name, b1, total = "syn1024", args.b1 or 3000000, args.curves * world
+    else:
+        name, b1, total = "syn2048", args.b1 or 11000000, (args.curves if args.curves != CURVES_PER_GPU else 8 * 14208)
+    b2 = 100 * b1
+    N = named_composite(name)
+    first, count = D.shard_range(total, rank, world)
+    peak_prod, peak_clk = E.measure_imad_peak(device)
+    ctx = E.EcmContext(N, count, device=device)
+    nl = ctx.nl
+    W = 2 * nl * nl + nl
+    tm = {}
+    sampler = ClockSampler(device)
+    L0 = E.lib().ecm_b200_launch_count()
+
+    def compute(first_sigma, cnt):
+        sig = [first_sigma + i for i in range(cnt)]
+        t0 = time.time()
+        ctx.build_curves(sig)
+        ctx.stage1(b1)
+        tm["s1_dev"] = ctx.last_timing()[0] / 1e3
+        x, z, f1 = ctx.read_stage1()
+        tm["s1_wall"] = time.time() - t0
+        t0 = time.time()
+        ctx.stage2(b1, b2)
+        tm["s2_dev"] = ctx.last_timing()[0] / 1e3
+        acc, f2, fail = ctx.read_stage2()
+        tm["s2_wall"] = time.time() - t0
+        tm["acc"] = (acc[0], acc[-1])
+        return {"save_lines": [E.save_line(sg, b1, N, xi, zi) for sg, xi, zi in zip(sig, x, z)],
+                "factors": [(sg, 1, f) for sg, f in zip(sig, f1) if f] + [(sg, 2, f) for sg, f in zip(sig, f2) if f]}
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t0 = time.time()
+    merged = D.run_sharded(total, SIGMA0, compute)
+    if dist:
+        dist.barrier()
+    wall = time.time() - t0
+    clocks = sampler.stop()
+    launches = E.lib().ecm_b200_launch_count() - L0
+    s1 = D.all_max(tm["s1_dev"]) if dist else tm["s1_dev"]
+    s2 = D.all_max(tm["s2_dev"]) if dist else tm["s2_dev"]
+    wall = D.all_max(wall) if dist else wall
+    launches = int(D.all_sum(launches)) if dist else launches
+    peak_all = D.all_sum(peak_prod) if dist else peak_prod
+    ctx.close()
+    if rank != 0:
+        return
+    import oracle_lib as O
+    o = O.ecm_curve(N, b1, b2, SIGMA0)
+    check = bool(merged["save_lines"][0] == o["save_line"] and tm["acc"][0] == o["acc"])
+    _, adds, dups = E.plan_stage1(b1)
+    mm1 = 6 * adds + 5 * dups
+    mm2, inv2, pairs2 = s2_program_modmuls(E, b1, b2)
+    line = {
+        "metric": "curves_per_sec_stage1_plus_stage2_B1_%g_%dbit" % (b1, N.bit_length()), "value": total / (s1 + s2), "unit": "curves/s",
+        "n_gpus": world, "steps": 1, "warmup": 0, "ms_per_step": (s1 + s2) * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.config == "syn2048_sweep" else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "%s: %d-bit composite, B1=%d, B2=%d, %d curves in one sigma range over %d GPU(s), stage 1 + stage 2" %
+                               (args.config, N.bit_length(), b1, b2, total, world), "composite": name, "b1": b1, "b2": b2, "curves_total": total,
+                   "limbs": nl, "first_curve_vs_oracle": check},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": total / wall, "unit": "curves/s", "what": "sigmas on host -> both stages -> save lines, factors and accumulators on host, merged on rank 0 (wall clock)",
+                "h2d_bytes_per_step": 32 * total, "d2h_bytes_per_step": (3 * nl * 4 + 2) * total},
+        "stage1": {"device_s": s1, "curves_per_sec": total / s1, "point_adds": adds, "point_doubles": dups, "modmul_per_curve": mm1,
+                   "products_per_sec": total / s1 * mm1 * W, "frac_of_imad_peak": total / s1 * mm1 * W / peak_all},
+        "stage2": {"device_s": s2, "curves_per_sec": total / s2, "modmul_per_curve": mm2, "inversions_per_curve": inv2, "pair_products_per_curve": pairs2,
+                   "products_per_sec": total / s2 * mm2 * W, "frac_of_imad_peak": total / s2 * mm2 * W / peak_all,
+                   "table_read_GBs_algorithmic": 2 * pairs2 * 4 * nl * total / s2 / 1e9 / world, "hbm_peak_GBs": 6540.8,
+                   "note": "every modular product of the compiled programs counted; inversions are extra work"},
+        "roofline": {"bound": "imad", "achieved": total / (s1 + s2) * (mm1 + mm2) * W / 1e9, "peak": peak_all / 1e9, "unit": "Gprod/s",
+                     "frac": total / (s1 + s2) * (mm1 + mm2) * W / peak_all, "traffic": None},
+        "merged_lines": len(merged["save_lines"]), "merged_sha256": hashlib.sha256("".join(merged["save_lines"]).encode()).hexdigest(),
+        "factors_found": len(merged["factors"]),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,6 +456,9 @@ def main():
     ap.add_argument("--curves", type=int, default=CURVES_PER_GPU, help="curves per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", default="syn415_s1", choices=["syn415_s1", "syn1024_s12", "syn2048_sweep"],
+                    help="syn415_s1: the headline line (default); the others run a BASELINE config at full size")
+    ap.add_argument("--b1", type=int, default=None, help="override B1 of a full-size config run")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -209,6 +497,12 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
+
+    if args.config != "syn415_s1":
+        full_config_run(args, E, torch, dist, rank, world, local_rank)
+        if dist:
+            dist.destroy_process_group()
+        return
 
     N = composite()
     curves = args.curves
@@ -302,24 +596,18 @@ def main():
         if not check:
             raise SystemExit("bench.py: stage-1 residues differ from the oracle")
 
-    # ---- the metric's second operand size: 1024-bit N, same B1, a few launches of the same schedule ----
+    # ---- the other BASELINE configs as bounded samples (rank 0) ----------------------------------------------------
     also = None
     if rank == 0 and not args.no_e2e:
-        N2 = int(json.load(open(os.path.join(ROOT, "tests", "golden", "composites.json")))["syn1024"])
-        c2 = E.EcmContext(N2, curves, device=local_rank)
-        c2.build_curves(sig)
-        c2.stage1_begin(B1)
-        tot2, _ = c2.stage1_launches()
-        c2.stage1_step(1); c2.sync()
-        c2.build_curves(sig); c2.stage1_begin(B1)
-        c2.timer_start(); c2.stage1_step(3); frac2 = c2.stage1_progress(); c2.timer_stop(); c2.sync()
-        ms2 = c2.timer_ms()
-        v2 = curves * frac2 / (ms2 / 1e3)
-        W2 = 2 * c2.nl * c2.nl + c2.nl
-        also = {"stage1_curves_per_sec_B1_1e6_1024bit": v2, "limbs": c2.nl, "launches_timed": 3, "launches_per_full_job": tot2,
-                "products_per_sec": v2 * MODMUL_PER_CURVE * W2, "frac_of_imad_peak": v2 * MODMUL_PER_CURVE * W2 / peak_prod,
-                "composite": "syn1024", "curves": curves}
-        c2.close()
+        also = {}
+        try:    # [2] 1024-bit, B1 = 3e6, 65 536 curves (stage 2: one wave of 32 768, tables 2.98 MB/curve)
+            also["config2_1024bit"] = config_sample(E, "syn1024", 3000000, curves, 32768, 3, 2000000, peak_prod, local_rank, (5000, 300000))
+        except Exception as e:          # a side measurement must never take the headline line down
+            also["config2_1024bit"] = {"error": repr(e)}
+        try:    # [4] 2048-bit, B1 = 1.1e7: one resident wave of the four-lanes-per-curve kernel
+            also["config4_2048bit"] = config_sample(E, "syn2048", 11000000, 14208, 4736, 3, 1000000, peak_prod, local_rank, (2000, 60000))
+        except Exception as e:
+            also["config4_2048bit"] = {"error": repr(e)}
         # stage-2 sample on the bench composite: B1=1e5 -> B2=1e7 (D=2310, U=16), all curves of this GPU
         sb1, sb2 = 100000, 10000000
         ctx.build_curves(sig)
@@ -329,11 +617,13 @@ def main():
         s2_wall = time.time() - t0
         s2_ms, s2_launches = ctx.last_timing()
         cnt = ctx.stage2_counters()
+        mm2, inv2, _ = s2_program_modmuls(E, sb1, sb2)
         table_bytes = (2 * cnt["s2_paired"]) * 4 * nl * curves          # Pa_inv + Pb operand of every pair step
         also["stage2_sample"] = {"b1": sb1, "b2": sb2, "curves": curves, "device_s": s2_ms / 1e3, "wall_s": s2_wall,
                                  "curves_per_sec": curves / (s2_ms / 1e3), "kernel_launches": s2_launches,
                                  "pair_steps": cnt["s2_paired"], "point_adds": cnt["s2_ptadds"], "inversions": cnt["s2_numinv"],
-                                 "products_per_sec_adds_and_pairs": curves * (6 * cnt["s2_ptadds"] + cnt["s2_paired"]) * W / (s2_ms / 1e3),
+                                 "modmul_per_curve": mm2, "inversions_per_curve": inv2,
+                                 "products_per_sec": curves * mm2 * W / (s2_ms / 1e3), "frac_of_imad_peak": curves * mm2 * W / (s2_ms / 1e3) / peak_prod,
                                  "table_read_GBs_algorithmic": table_bytes / (s2_ms / 1e3) / 1e9,
                                  "hbm_peak_GBs": 6540.8}
         # special-form input (N | 2^415-1): the shift-and-fold kernels next to the Montgomery kernels on the same base
@@ -367,6 +657,19 @@ def main():
         finally:
             os.environ.pop("ECM_B200_NO_FOLD", None)
 
+    # ---- strong-scaling sweep sample (every rank takes part) and the CLI's own multi-GPU path -----------------------
+    sweep = None
+    if not args.no_e2e:
+        try:
+            sweep = sweep_sample(E, torch, dist, rank, world, local_rank, 8 * 14208, 10000)
+        except Exception as e:
+            sweep = {"error": repr(e)}
+        if rank == 0 and also is not None:
+            also["sweep"] = sweep
+            if world > 1:
+                also["cli_multi_gpu"] = cli_multi_gpu_check(world)
+        barrier()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, kind, cores, desc = run_reference_sample(B1, host_threads())
@@ -385,10 +688,10 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches,
             "roofline": {"bound": "imad", "achieved": prod_rate / 1e9, "peak": peak_all / 1e9, "unit": "Gprod/s",
                          "frac": prod_rate / peak_all,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (33.47 + 56.40 MB: the batch state is
-                         # re-read after the L2 flush between steps and dirty lines are written back),
-                         # profiles/r1_final_stage1_ncu_full_summary.txt; incidental for an IMAD-bound kernel
-                         "traffic": 89868544,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, read from the committed
+                         # ncu summary of the same command (the batch state re-read after the L2 flush + write-backs;
+                         # incidental for an IMAD-bound kernel); null when that file is absent
+                         "traffic": profile_traffic(), "traffic_source": PROFILE_SUMMARY,
                          "note": "achieved = curves/s x 12974547 modmul/curve x (2n^2+n) products, n=%d; peak = fastest of three live probes on this GPU "
                                  "(IMAD.WIDE.U32.X chains with uniform / per-thread multiplier, register-resident 32-limb Montgomery loop) "
                                  "at %.0f MHz; the pipe's arithmetic ceiling is 32 products/clk/SM" % (nl, peak_clk)},

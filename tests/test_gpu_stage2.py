@@ -263,3 +263,38 @@ def test_cli_random_sigmas_are_valid_resume_lines(tmp_path):
         sig = [int(re.search(r"SIGMA=(\d+)", l).group(1)) for l in lines]
         assert len(lines) == 12 and len(set(sig)) == 12 and min(sig) >= 6
         assert [check_line(l, expect_n=N) for l in lines] == ["ok"] * 12
+
+
+def _next_prime(n):
+    n |= 1
+    while not all(pow(a, n - 1, n) == 1 for a in (2, 3, 5, 7, 11, 13)):      # Fermat tests: plenty for a test modulus
+        n += 2
+    return n
+
+
+@pytest.mark.parametrize("bits", [1100, 2000])
+def test_cooperative_stage2_equals_one_thread_stage2_and_oracle(bits, monkeypatch):
+    """48 / 64 limbs: stage 2 on the four-lanes-per-curve layout (coop_s2.cuh: striped tables, pair loop with register
+    accumulators, inverse by the group's lane 0) against the one-thread-per-curve kernels and the oracle -- on a composite
+    with a 30-bit prime factor, so that inversions FAIL on some curves (foundDuringInv path, lane-0 semantics) and
+    factors are found in both stages."""
+    N = 1000000007 * _next_prime((1 << bits) + 12345)
+    b1, b2, count = 3000, 300000, 40
+    sig = [11 + i for i in range(count)]
+    res = {}
+    for kern in ("coop", "solo"):
+        monkeypatch.setenv("ECM_B200_S2_KERNEL", kern)
+        ctx = E.EcmContext(N, count)
+        try:
+            ctx.build_curves(sig); ctx.stage1(b1)
+            ctx.stage2(b1, b2)
+            res[kern] = ctx.read_stage2()
+        finally:
+            ctx.close()
+    assert res["coop"] == res["solo"]
+    acc, f2, fail = res["coop"]
+    assert any(fail) and not all(fail) and any(f2)
+    picks = [i for i in range(count) if fail[i]][:3] + [i for i in range(count) if not fail[i]][:3]
+    for i in picks:
+        o = O.ecm_curve(N, b1, b2, sig[i])
+        assert (acc[i], f2[i]) == (o["acc"], o["f2"]), i
