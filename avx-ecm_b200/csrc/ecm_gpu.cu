@@ -254,9 +254,6 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e_); ecm_b200_destroy(c); return fail(ECM_B200_ECUDA, m); } } while (0)
     CUC(cudaSetDevice(device));
     CUC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-    CUC(eng->prepare());
-    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CUC(cudaEventCreate(&c->ev0)); CUC(cudaEventCreate(&c->ev1));
     // Which stage-1 kernel: the register-resident macro-op machine (rv.cuh) where it is compiled for this limb count --
     // one thread per curve up to 16 limbs, four lanes per curve at 48/64 limbs -- else the slot-file machine (vm.cuh).
     // The fold kernel set keeps the slot-file machine (it wants more warps than the rv register budget allows).
@@ -272,6 +269,9 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
         if (const char *e = getenv("ECM_B200_S2_KERNEL")) { if (!strcmp(e, "solo")) cs2 = false; }
         eng->use_coop_s2 = cs2;
     }
+    CUC(eng->prepare());
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->ev0)); CUC(cudaEventCreate(&c->ev1));
     // Curves per group (= one stage-1 block).  Whole multiples of 4 warps keep the four SM
     // sub-partitions evenly loaded (14 warps = 4,4,3,3 measured 6.9 Tprod/s vs 7.2 with 12).  More
     // resident warps hide more latency (throughput ~ w/(w+3.6), measured 12..24 warps), but a batch
@@ -298,7 +298,7 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
         c->threads_s1 = bestT;
         c->T = bestT / Lc;
         c->groups_max = (max_curves + c->T - 1) / c->T;
-        const uint32_t stride = eng->use_rv ? (uint32_t)eng->rv_max_threads : (uint32_t)eng->stride_for_threads(bestT);
+        const uint32_t stride = (uint32_t)eng->stride_for_threads(bestT);
         c->G1 = Geom{c->T, stride, NSLOT_S1, Lc};
     }
     c->state_words = (size_t)c->groups_max * NSLOT_S1 * (nl / c->G1.L) * c->G1.stride;
@@ -638,7 +638,9 @@ static int run_program(ecm_b200_ctx *c, const std::vector<uint64_t> &host_code, 
                 if (rc) return rc;
                 {   // chunk-major (group, chunk) items, at most one resident wave per launch
                     const uint32_t TP = (uint32_t)c->eng->threads_pair, npairs = (uint32_t)(j - i);
-                    const uint32_t pgroups = (ncurves + TP - 1) / TP, pchunk = 512;
+                    uint32_t pchunk = 512;
+                    if (const char *e = getenv("ECM_B200_PAIR_CHUNK")) { const int v = atoi(e); if (v >= 16) pchunk = (uint32_t)v; }
+                    const uint32_t pgroups = (ncurves + TP - 1) / TP;
                     const uint64_t items = (uint64_t)((npairs + pchunk - 1) / pchunk) * pgroups;
                     const uint32_t per = std::min<uint32_t>(pgroups, (uint32_t)(c->num_sms * c->eng->pair_blocks_per_sm));
                     for (uint64_t it = 0; it < items;) {

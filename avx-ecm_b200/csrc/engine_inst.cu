@@ -9,17 +9,23 @@
 #endif
 
 #include <type_traits>
+#include <cstdlib>
 namespace ecmb200 {
 inline namespace ECM_VNS {
 
 // which field policy the register-resident stage-1 machine (rv.cuh) uses for a limb count, if any: one thread per curve
 // up to 16 limbs (four operand values + two accumulator pairs fit the registers of a 384-thread block), four lanes per
 // curve at 48 and 64 limbs (coop.cuh).  20-32 limbs keep the slot-file machine (dedicated squaring, 0.92 of the roof).
-template <int NL, class Enable = void> struct RvCfg { static constexpr int MAXT = 0; typedef void Field; };
-template <int NL> struct RvCfg<NL, typename std::enable_if<(NL <= 16)>::type> { static constexpr int MAXT = 384; typedef SoloField<NL> Field; };
+// MAXT = block size (= lane stride) of the standard instance; BIG = a second instance for batches that fill larger blocks,
+// where the registers allow it (96 / 119 registers at 10 / 13 limbs), 0 = none.
+template <int NL, class Enable = void> struct RvCfg { static constexpr int MAXT = 0, BIG = 0; typedef void Field; };
+template <int NL> struct RvCfg<NL, typename std::enable_if<(NL <= 16)>::type> {
+    static constexpr int MAXT = 384, BIG = (NL <= 10) ? 640 : (NL <= 13) ? 512 : 0;
+    typedef SoloField<NL> Field;
+};
 #if !ECM_SPECIAL
-template <> struct RvCfg<48> { static constexpr int MAXT = 384; typedef CoopField<12, 4> Field; };
-template <> struct RvCfg<64> { static constexpr int MAXT = 384; typedef CoopField<16, 4> Field; };
+template <> struct RvCfg<48> { static constexpr int MAXT = 384, BIG = 0; typedef CoopField<12, 4> Field; };
+template <> struct RvCfg<64> { static constexpr int MAXT = 384, BIG = 0; typedef CoopField<16, 4> Field; };
 #endif
 // stage 2 on the cooperative layout (coop_s2.cuh) where stage 1 has it
 template <int NL> struct S2CoopCfg { static constexpr int M = 0, L = 1; };
@@ -39,7 +45,7 @@ struct EngineT : Engine {
         nl = NL; stride_s1 = S1Cfg<NL>::STRIDE; smem_s1 = S1Cfg<NL>::smem;
         params_bytes = sizeof(ModParams<NL>);
         threads_s2 = S2Cfg<NL>::THREADS; smem_s2 = S2Cfg<NL>::smem; nslot_s2 = NSLOT_S2;
-        rv_max_threads = RvCfg<NL>::MAXT; rv_lanes = RvLanes<typename RvCfg<NL>::Field>::L;
+        rv_max_threads = RvCfg<NL>::BIG ? RvCfg<NL>::BIG : RvCfg<NL>::MAXT; rv_lanes = RvLanes<typename RvCfg<NL>::Field>::L;
         has_coop_s2 = S2CoopCfg<NL>::M != 0;
     }
     void set_params(const Big &n, const Big &one, const Big &r2, const Big &r3, const Big &rri, const Big &rref, uint32_t m0inv) override
@@ -52,7 +58,11 @@ struct EngineT : Engine {
     {
         return ECM_SPECIAL && NL <= 32 && kbits >= 64 && (int)(kbits >> 5) >= SpecialRange<NL>::LOW && (int)(kbits >> 5) < NL;
     }
-    int stride_for_threads(uint32_t T) const override { return T <= (uint32_t)S1Small<NL>::MAXT ? S1Small<NL>::MAXT : S1Cfg<NL>::STRIDE; }
+    int stride_for_threads(uint32_t T) const override
+    {
+        if (use_rv) return (RvCfg<NL>::BIG && T > (uint32_t)RvCfg<NL>::MAXT) ? RvCfg<NL>::BIG : RvCfg<NL>::MAXT;
+        return T <= (uint32_t)S1Small<NL>::MAXT ? S1Small<NL>::MAXT : S1Cfg<NL>::STRIDE;
+    }
     const void *params_host() const override { return &P; }
     void set_params_device(const void *d) override { Pg = static_cast<const ModParams<NL> *>(d); }
     cudaError_t prepare() override
@@ -68,6 +78,10 @@ struct EngineT : Engine {
             typedef typename RvCfg<NL>::Field F;
             e = cudaFuncSetAttribute(k_stage1_rv<F, RvCfg<NL>::MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * F::M * 4 * RvCfg<NL>::MAXT);
             if (e != cudaSuccess) return e;
+            if constexpr (RvCfg<NL>::BIG != 0) {
+                e = cudaFuncSetAttribute(k_stage1_rv<F, RvCfg<NL>::BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * F::M * 4 * RvCfg<NL>::BIG);
+                if (e != cudaSuccess) return e;
+            }
         }
         if constexpr (S2CoopCfg<NL>::M != 0) {
             if (use_coop_s2) {
@@ -82,9 +96,13 @@ struct EngineT : Engine {
             }
         }
         threads_pair = PairCfg<NL>::THREADS;
+        if (NL <= 16) if (const char *ev = getenv("ECM_B200_PAIR_THREADS")) if (atoi(ev) == 384) threads_pair = 384;   // experiment
         use_pair_kernel = (NL <= 32);
         if (!use_pair_kernel) return cudaFuncSetAttribute(k_vm2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
-        if constexpr (NL <= 32) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pair_blocks_per_sm, k_pair<NL>, threads_pair, 0);
+        if constexpr (NL <= 16) {
+            if (threads_pair == 384) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pair_blocks_per_sm, k_pair<NL, 384>, 384, 0);
+            else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pair_blocks_per_sm, k_pair<NL>, threads_pair, 0);
+        } else if constexpr (NL <= 32) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pair_blocks_per_sm, k_pair<NL>, threads_pair, 0);
         if (e != cudaSuccess) return e;
         if (pair_blocks_per_sm < 1) pair_blocks_per_sm = 1;
         return cudaFuncSetAttribute(k_vm2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
@@ -112,6 +130,13 @@ struct EngineT : Engine {
                 uint32_t nlanes = (ncurves * L + 31) / 32 * 32;
                 if (nlanes > cap * L) nlanes = cap * L;
                 k_pair_coop<M, L><<<blocks, CoopS2Cfg<M, L>::PAIR_THREADS, 0, st>>>(P, state2, cap, tab, code, npairs, nlanes, chunk_len, groups, item0);
+                count_launch();
+                return;
+            }
+        }
+        if constexpr (NL <= 16) {
+            if (threads_pair == 384) {
+                k_pair<NL, 384><<<blocks, 384, 0, st>>>(P, state2, cap, tab, code, npairs, ncurves, chunk_len, groups, item0);
                 count_launch();
                 return;
             }
@@ -155,6 +180,13 @@ struct EngineT : Engine {
         if constexpr (RvCfg<NL>::MAXT != 0) {
             if (use_rv) {
                 typedef typename RvCfg<NL>::Field F;
+                if constexpr (RvCfg<NL>::BIG != 0) {
+                    if (threads > (uint32_t)RvCfg<NL>::MAXT) {
+                        k_stage1_rv<F, RvCfg<NL>::BIG><<<blocks, threads, 2 * F::M * 4 * RvCfg<NL>::BIG, st>>>(P, state, ops, nops, chunk_len, groups, item0);
+                        count_launch();
+                        return;
+                    }
+                }
                 k_stage1_rv<F, RvCfg<NL>::MAXT><<<blocks, threads, 2 * F::M * 4 * RvCfg<NL>::MAXT, st>>>(P, state, ops, nops, chunk_len, groups, item0);
                 count_launch();
                 return;

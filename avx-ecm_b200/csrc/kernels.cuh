@@ -481,8 +481,8 @@ struct PairCfg {
 // so that every SM always holds its full complement of blocks even when the batch is not a multiple of
 // the resident wave.  The product of a run is commutative, so splitting it over two accumulators (and
 // re-joining them at the end of the chunk) yields the identical canonical residue.
-template <int NL>
-__global__ void __launch_bounds__(PairCfg<NL>::THREADS)
+template <int NL, int PT = PairCfg<NL>::THREADS>
+__global__ void __launch_bounds__(PT, (PT >= 384) ? 1 : 0)
 k_pair(const ModParams<NL> P, uint32_t *__restrict__ state2, uint32_t cap, const uint32_t *__restrict__ tab,
        const uint64_t *__restrict__ code, uint32_t npairs, uint32_t ncurves, uint32_t chunk_len, uint32_t groups, uint64_t item0)
 {
@@ -490,7 +490,7 @@ k_pair(const ModParams<NL> P, uint32_t *__restrict__ state2, uint32_t cap, const
     const uint64_t item = item0 + blockIdx.x;
     const uint32_t g = (uint32_t)(item % groups);
     const uint32_t chunk = (uint32_t)(item / groups);
-    const uint32_t curve = g * PairCfg<NL>::THREADS + threadIdx.x;
+    const uint32_t curve = g * PT + threadIdx.x;
     if (curve >= ncurves) return;
     uint32_t i = chunk * chunk_len;
     const uint32_t end = (i + chunk_len < npairs) ? i + chunk_len : npairs;

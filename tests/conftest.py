@@ -40,8 +40,13 @@ def is_known_answer(name):
     return name.startswith(("readme508_b1_1e6", "t35_full_", "csh_line", "slow_csh_line", "syn1024_b1_1e5", "syn2048_b1_5e4"))
 
 
+# test.csh lines whose 8 curves keep one warp busy for 1.5-4 minutes (B1 = 3e6, B2 up to 1e9, 24-limb inputs): with the
+# "slow_" cases they run under ECM_B200_SLOW=1 (log of such a run on the GPU: profiles/r2_known_answers_all.log)
+HEAVY = ("csh_line02", "csh_line09", "csh_line11", "csh_line14", "csh_line22", "csh_line25")
+
+
 def is_slow(name):
-    return name.startswith("slow_")
+    return name.startswith("slow_") or name in HEAVY
 
 
 def golden_factor(g, sigma, stage):
