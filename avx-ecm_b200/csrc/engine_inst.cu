@@ -95,8 +95,10 @@ struct EngineT : Engine {
                 return cudaFuncSetAttribute(k_vm2_coop<S2CoopCfg<NL>::M, S2CoopCfg<NL>::L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
             }
         }
-        threads_pair = PairCfg<NL>::THREADS;
-        if (NL <= 16) if (const char *ev = getenv("ECM_B200_PAIR_THREADS")) if (atoi(ev) == 384) threads_pair = 384;   // experiment
+        // pair kernel: one 384-thread block per SM up to 16 limbs (measured at 415 bits, B1=1e6/B2=1e8, 65 536 curves:
+        // stage 2 in 12.44 s against 13.76 s with three 128-thread blocks per SM), 128-thread blocks above
+        threads_pair = (NL <= 16) ? 384 : PairCfg<NL>::THREADS;
+        if (NL <= 16) if (const char *ev = getenv("ECM_B200_PAIR_THREADS")) if (atoi(ev) == 128) threads_pair = 128;
         use_pair_kernel = (NL <= 32);
         if (!use_pair_kernel) return cudaFuncSetAttribute(k_vm2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s2);
         if constexpr (NL <= 16) {

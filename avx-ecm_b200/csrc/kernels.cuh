@@ -7,6 +7,12 @@
 #include "geom.hpp"
 #include "vm.cuh"
 #include "modinv.cuh"
+#include "modinv_fast.hpp"
+
+// ECM_FAST_INV = 1 (default): word-batched inverse / gcd (modinv_fast.hpp); 0: the bit-serial routine of modinv.cuh
+#ifndef ECM_FAST_INV
+#define ECM_FAST_INV 1
+#endif
 
 namespace ecmb200 {
 inline namespace ECM_VNS {
@@ -131,6 +137,9 @@ __device__ __noinline__ void nm_addsub(uint32_t *r, const uint32_t *a, const uin
 template <int NL>
 __device__ __noinline__ bool nm_inverse(uint32_t *inv, uint32_t *g, const uint32_t *x, const ModParams<NL> *Pg)
 {
+#if ECM_FAST_INV
+    return fastinv::mod_inverse<NL, true>(inv, g, x, Pg->n);
+#else
     uint32_t a[NL], i[NL], gg[NL];
 #pragma unroll
     for (int k = 0; k < NL; k++) a[k] = x[k];
@@ -138,17 +147,22 @@ __device__ __noinline__ bool nm_inverse(uint32_t *inv, uint32_t *g, const uint32
 #pragma unroll
     for (int k = 0; k < NL; k++) { inv[k] = i[k]; g[k] = gg[k]; }
     return ok;
+#endif
 }
 // g = gcd(x, m) for an odd m of NL limbs in global memory (x need not be below m)
 template <int NL>
 __device__ __noinline__ void nm_gcd(uint32_t *g, const uint32_t *x, const uint32_t *m)
 {
+#if ECM_FAST_INV
+    fastinv::mod_inverse<NL, false>(nullptr, g, x, m);
+#else
     uint32_t a[NL], i[NL], gg[NL];
 #pragma unroll
     for (int k = 0; k < NL; k++) a[k] = x[k];
     mod_inverse<NL, false>(i, gg, a, m);
 #pragma unroll
     for (int k = 0; k < NL; k++) g[k] = gg[k];
+#endif
 }
 
 // ---- curve set-up -----------------------------------------------------------------------------

@@ -291,10 +291,14 @@ def test_cooperative_stage2_equals_one_thread_stage2_and_oracle(bits, monkeypatc
             res[kern] = ctx.read_stage2()
         finally:
             ctx.close()
-    assert res["coop"] == res["solo"]
     acc, f2, fail = res["coop"]
+    sacc, sf2, sfail = res["solo"]
+    assert fail == sfail, [i for i in range(count) if fail[i] != sfail[i]]
+    assert f2 == sf2, [i for i in range(count) if f2[i] != sf2[i]]
+    diff = [i for i in range(count) if acc[i] != sacc[i]]
+    assert not diff, (diff, [fail[i] for i in diff])
     assert any(fail) and not all(fail) and any(f2)
     picks = [i for i in range(count) if fail[i]][:3] + [i for i in range(count) if not fail[i]][:3]
     for i in picks:
         o = O.ecm_curve(N, b1, b2, sig[i])
-        assert (acc[i], f2[i]) == (o["acc"], o["f2"]), i
+        assert (acc[i], f2[i]) == (o["acc"], o["f2"]), (i, fail[i])
