@@ -74,7 +74,13 @@ __device__ __noinline__ bool coop_inverse(uint32_t (&d)[M], const uint32_t (&x)[
     }
     failed = cm.shfl(failed, 0);
     coop_scatter<M, L>(d, t, cm);
-    if (failed) coop_scatter<M, L>(acc, ac, cm);
+    // every lane of the warp takes part in every shuffle: a warp holds 32/L curves and only some of them may have failed
+    uint32_t na[M];
+    coop_scatter<M, L>(na, ac, cm);
+    if (failed) {
+#pragma unroll
+        for (int j = 0; j < M; j++) acc[j] = na[j];
+    }
     return failed != 0;
 }
 
