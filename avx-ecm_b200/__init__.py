@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.realpath(__file__))
-LIB_PATH = os.path.join(_HERE, "libecm_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("ECM_B200_LIB", "libecm_b200.so"))     # ECM_B200_LIB: A/B builds of the same library
 _lib = None
 
 u8p = ctypes.POINTER(ctypes.c_uint8)

@@ -18,8 +18,11 @@ inline namespace ECM_VNS {
 // curve at 48 and 64 limbs (coop.cuh).  20-32 limbs keep the slot-file machine (dedicated squaring, 0.92 of the roof).
 // MAXT = block size (= lane stride) of the standard instance; BIG = a second instance for batches that fill larger blocks,
 // where the registers allow it (96 / 119 registers at 10 / 13 limbs), 0 = none.
+#ifndef RV_SOLO_MAX
+#define RV_SOLO_MAX 16
+#endif
 template <int NL, class Enable = void> struct RvCfg { static constexpr int MAXT = 0, BIG = 0; typedef void Field; };
-template <int NL> struct RvCfg<NL, typename std::enable_if<(NL <= 16)>::type> {
+template <int NL> struct RvCfg<NL, typename std::enable_if<(NL <= RV_SOLO_MAX)>::type> {
     static constexpr int MAXT = 384, BIG = (NL <= 10) ? 640 : (NL <= 13) ? 512 : 0;
     typedef SoloField<NL> Field;
 };
