@@ -112,6 +112,7 @@ k_vm2_coop(const ModParams<M * L> P, const ModParams<M * L> *Pg, uint32_t *__res
 #pragma unroll 1
     for (; i < end; i++) {
         const uint64_t ins = __ldg(code + i);
+        vm2_lookahead<M>(code, i, end, tab, nwl, lane);
         const uint32_t lo = (uint32_t)ins, imm = (uint32_t)(ins >> 32);
         const uint32_t op = lo & 0xffu, d = (lo >> 8) & 0xffu, x = (lo >> 16) & 0xffu, y = lo >> 24;
         if (op == V2_MUL2) {

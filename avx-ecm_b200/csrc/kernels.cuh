@@ -35,6 +35,31 @@ __device__ __forceinline__ void tload(uint32_t (&r)[NL], const uint32_t *tab, si
 #pragma unroll
     for (int k = 0; k < NL; k++) r[k] = p[k * 32];
 }
+// hint the NL lines of a table operand into L2/L1 ahead of its use (one 128-byte line per limb and warp)
+template <int NL>
+__device__ __forceinline__ void tprefetch(const uint32_t *tab, size_t base)
+{
+    const uint32_t *p = tab + base;
+#pragma unroll
+    for (int k = 0; k < NL; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + k * 32));
+}
+// The slot machine executes `ldg; mul; stg` sequences of the batch inversions with the table in HBM and only 8-12 warps
+// per SM: ncu showed 1.7 "long scoreboard" stall cycles per issued instruction (55 % fmaheavy).  Looking a few
+// instructions ahead and prefetching the operands of the next table read hides that latency behind the current product.
+template <int NL>
+__device__ __forceinline__ void vm2_lookahead(const uint64_t *code, uint64_t i, uint64_t end, const uint32_t *tab, uint32_t nwg, uint32_t lane)
+{
+    constexpr int AHEAD = 3;
+    if (i + AHEAD < end) {
+        const uint64_t ins = __ldg(code + i + AHEAD);
+        const uint32_t op = (uint32_t)ins & 0xffu, imm = (uint32_t)(ins >> 32);
+        if (op == 6u /* V2_LDG */) tprefetch<NL>(tab, tab_base(imm, nwg, lane, NL));
+        else if (op == 10u /* V2_PAIR */) {
+            tprefetch<NL>(tab, tab_base(imm & 0xffffu, nwg, lane, NL));
+            tprefetch<NL>(tab, tab_base(imm >> 16, nwg, lane, NL));
+        }
+    }
+}
 template <int NL>
 __device__ __forceinline__ void tstore(uint32_t *tab, size_t base, const uint32_t (&r)[NL])
 {
@@ -370,7 +395,10 @@ __device__ __noinline__ void vm2_inverse(uint32_t *dptr, const uint32_t *xptr, u
 template <int NL>
 struct S2Cfg {
     // measured: +21 % at 32 limbs (128 -> 256 threads per SM), -3 % at 13 limbs where 256 threads fit anyway
-    static constexpr bool HYBRID = (NL >= 20 && NL <= 32);
+#ifndef ECM_S2_HYBRID_SMALL
+#define ECM_S2_HYBRID_SMALL 0
+#endif
+    static constexpr bool HYBRID = (NL >= 20 && NL <= 32) || (ECM_S2_HYBRID_SMALL && NL <= 16);
     static constexpr int nsmem = HYBRID ? (NSLOT_S2 - NGLOBAL_S2) : NSLOT_S2;
     static constexpr int per_thread = nsmem * NL * 4;
     static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;
@@ -409,6 +437,7 @@ k_vm2(const ModParams<NL> P, const ModParams<NL> *Pg, uint32_t *__restrict__ sta
 #pragma unroll 1
     for (; i < end; i++) {
         const uint64_t ins = __ldg(code + i);
+        vm2_lookahead<NL>(code, i, end, tab, nwg, curve);
         const uint32_t lo = (uint32_t)ins, imm = (uint32_t)(ins >> 32);
         const uint32_t op = lo & 0xffu, d = (lo >> 8) & 0xffu, x = (lo >> 16) & 0xffu, y = lo >> 24;
         if (op == V2_MUL2) {

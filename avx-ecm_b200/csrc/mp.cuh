@@ -22,9 +22,6 @@
 #ifndef ECM_SPECIAL
 #define ECM_SPECIAL 0
 #endif
-#ifndef ECM_SP_DUAL
-#define ECM_SP_DUAL 0
-#endif
 #if ECM_SPECIAL
 #define ECM_VNS sp
 #else
@@ -124,44 +121,6 @@ __device__ __forceinline__ void full_mul(uint32_t (&T)[2 * NL], const uint32_t (
     T[2 * NL - 1] = addc3(E[NL], O[NL - 1]);
 }
 
-// Two independent double-length products with their rows interleaved (T0 = a0*b0, T1 = a1*b1): four carry chains in
-// flight instead of two, for the fold kernels, whose products have no reduction rows to overlap with.
-template <int NL>
-__device__ __forceinline__ void full_mul2(uint32_t (&T0)[2 * NL], const uint32_t (&a0)[NL], const uint32_t (&b0)[NL],
-                                          uint32_t (&T1)[2 * NL], const uint32_t (&a1)[NL], const uint32_t (&b1)[NL])
-{
-    constexpr int W = MontW<NL>::W;
-    uint32_t X0[W], Y0[W], X1[W], Y1[W];
-#pragma unroll
-    for (int k = 0; k < W; k++) { X0[k] = 0; Y0[k] = 0; X1[k] = 0; Y1[k] = 0; }
-    auto row = [&](uint32_t (&Eo)[W], uint32_t (&Oo)[W], const uint32_t (&a)[NL], uint32_t bi, uint32_t &low) {
-        uint32_t e1 = Eo[1];
-#pragma unroll
-        for (int k = 0; k < W - 2; k++) Eo[k] = Eo[k + 2];
-        Eo[W - 2] = 0; Eo[W - 1] = 0;
-        add_cc(Oo[0], e1);
-        if (NL > 1) mad_row<NL, W, 1, true>(Eo, a, bi);
-        else { addc_cc(Eo[0], 0); addc(Eo[1], 0); }
-        mad_row<NL, W, 0, false>(Oo, a, bi);
-        low = Oo[0];
-    };
-#pragma unroll
-    for (int i = 0; i < NL; i++) {
-        if ((i & 1) == 0) { row(X0, Y0, a0, b0[i], T0[i]); row(X1, Y1, a1, b1[i], T1[i]); }
-        else { row(Y0, X0, a0, b0[i], T0[i]); row(Y1, X1, a1, b1[i], T1[i]); }
-    }
-    auto high = [&](uint32_t (&T)[2 * NL], uint32_t (&X)[W], uint32_t (&Y)[W]) {
-        uint32_t (&E)[W] = (NL % 2 == 0) ? X : Y;
-        uint32_t (&O)[W] = (NL % 2 == 0) ? Y : X;
-        T[NL] = add3_cc(E[1], O[0]);
-#pragma unroll
-        for (int k = 1; k < NL - 1; k++) T[NL + k] = addc3_cc(E[k + 1], O[k]);
-        T[2 * NL - 1] = addc3(E[NL], O[NL - 1]);
-    };
-    high(T0, X0, Y0);
-    high(T1, X1, Y1);
-}
-
 // r = a*b mod N for a special-form N (P.kind/kbits/cval), canonical
 template <int NL>
 __device__ __forceinline__ void special_mul(uint32_t (&r)[NL], const uint32_t (&a)[NL], const uint32_t (&b)[NL],
@@ -237,18 +196,13 @@ __device__ __forceinline__ void mont_mul2(uint32_t (&r0)[NL], const uint32_t (&a
 {
 #if ECM_SPECIAL
     {
-#if ECM_SP_DUAL
-        uint32_t T0[2 * NL], T1[2 * NL];                   // both products read all operands before either result is written
-        full_mul2<NL>(T0, a0, b0, T1, a1, b1);
-        special_fold<NL>(r0, T0, P.kbits, P.kind, P.cval);
-        special_fold<NL>(r1, T1, P.kbits, P.kind, P.cval);
-#else
+        // (interleaving the rows of the two double-length products was tried and changed nothing: 88.5 k curves/s at
+        // 2^415-1 either way -- the fold kernels are bound by the dependent chains of the fold itself)
         uint32_t t0[NL];                                   // r0 may alias a1/b1
         special_mul<NL>(t0, a0, b0, P);
         special_mul<NL>(r1, a1, b1, P);
 #pragma unroll
         for (int k = 0; k < NL; k++) r0[k] = t0[k];
-#endif
         return;
     }
 #endif
