@@ -18,8 +18,10 @@ inline namespace ECM_VNS {
 // curve at 48 and 64 limbs (coop.cuh).  20-32 limbs keep the slot-file machine (dedicated squaring, 0.92 of the roof).
 // MAXT = block size (= lane stride) of the standard instance; BIG = a second instance for batches that fill larger blocks,
 // where the registers allow it (96 / 119 registers at 10 / 13 limbs), 0 = none.
+// one thread per curve: up to 16 limbs with the dual product; 20 and 24 limbs with two single products per phase (144 / 168
+// registers), measured 7.16 -> 7.78 and 6.92 -> 7.43 Tprod/s against the slot-file machine with its dedicated squaring
 #ifndef RV_SOLO_MAX
-#define RV_SOLO_MAX 16
+#define RV_SOLO_MAX (ECM_SPECIAL ? 16 : 24)
 #endif
 template <int NL, class Enable = void> struct RvCfg { static constexpr int MAXT = 0, BIG = 0; typedef void Field; };
 template <int NL> struct RvCfg<NL, typename std::enable_if<(NL <= RV_SOLO_MAX)>::type> {
