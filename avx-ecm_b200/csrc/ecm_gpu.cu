@@ -167,6 +167,9 @@ struct ecm_b200_ctx {
     size_t s2_tab_bytes = 0, s2_state_bytes = 0, s2_code_bytes = 0; uint32_t s2_fail_cap = 0;
     uint32_t s2_cap = 0, s2_first = 0, s2_n = 0, s2_groups = 0;      // current wave
     bool s2_open = false;       // ecm_b200_stage2_init done: tables resident, ecm_b200_stage2_range may follow
+    // ECM_B200_S2_TRACE=1: device time of stage 2 split by kernel kind (event pairs around every segment), printed to stderr
+    bool s2_trace = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> s2_marks;     // kind (0 = slot machine, 1 = pair kernel), begin, end
 };
 
 extern "C" {
@@ -312,6 +315,7 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
     CUC(cudaMalloc(&c->d_params, eng->params_bytes));
     CUC(cudaMemcpyAsync(c->d_params, eng->params_host(), eng->params_bytes, cudaMemcpyHostToDevice, c->stream));
     eng->set_params_device(c->d_params);
+    c->s2_trace = getenv("ECM_B200_S2_TRACE") != nullptr;
     CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
     *out = c;
@@ -601,16 +605,53 @@ int ecm_b200_read_stage1(ecm_b200_ctx *c, uint32_t *x, uint32_t *z, uint8_t *fac
     return ECM_B200_OK;
 }
 
+struct S2Mark {        // one traced segment (no-op unless the context traces)
+    ecm_b200_ctx *c; cudaEvent_t e0 = nullptr, e1 = nullptr; int kind;
+    S2Mark(ecm_b200_ctx *c_, int kind_) : c(c_), kind(kind_) {
+        if (!c->s2_trace) return;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream);
+    }
+    ~S2Mark() { if (e0) { cudaEventRecord(e1, c->stream); c->s2_marks.push_back({kind, {e0, e1}}); } }
+};
+
+// after a stream synchronize: sum and print the traced segments
+static void s2_trace_report(ecm_b200_ctx *c, const char *what)
+{
+    if (!c->s2_trace) return;
+    double ms[2] = {0, 0}; size_t n[2] = {0, 0};
+    for (auto &m : c->s2_marks) {
+        float t = 0; cudaEventElapsedTime(&t, m.second.first, m.second.second);
+        ms[m.first] += t; n[m.first]++;
+        cudaEventDestroy(m.second.first); cudaEventDestroy(m.second.second);
+    }
+    c->s2_marks.clear();
+    fprintf(stderr, "[ecm_b200 s2 trace] %s: slot machine %.1f ms in %zu segments, pair kernel %.1f ms in %zu segments\n", what, ms[0], n[0], ms[1], n[1]);
+}
+
 // Generic part of a stage-2 program: the slot-file machine over a wave of `groups` curve groups with the
 // same round-robin (group, chunk) schedule as stage 1.
 static int run_vm2(ecm_b200_ctx *c, const uint64_t *d_code, uint64_t ncode, uint32_t *state2, uint32_t cap2, uint32_t *tab,
                    uint32_t groups, uint8_t *inv_fail)
 {
     if (ncode == 0) return ECM_B200_OK;
-    const uint32_t chunk = 65536;
+    S2Mark mark(c, 0);
+    const uint32_t per = std::min<uint32_t>(groups, (uint32_t)c->num_sms);
+    // Items are (group, chunk), chunk-major, at most `per` per launch.  With more groups than SMs one chunk per segment
+    // leaves the last launch of every segment part empty (256 groups on 148 SMs: 148 + 108 blocks, 86 % of the machine);
+    // cutting the segment into k chunks lets the launches interleave groups of neighbouring chunks, so that only the very
+    // last launch is short.  k = the split (at least 32 instructions per chunk) that wastes the fewest block slots.
+    uint32_t k = 1;
+    if (groups > per) {
+        double best = 0;
+        for (uint32_t t = 1; t <= 16 && ncode / t >= 32; t++) {
+            const uint64_t it = (uint64_t)groups * t, launches = (it + per - 1) / per;
+            const double eff = (double)it / (double)(launches * per) - 0.002 * t;       // small price per extra chunk (slot reloads)
+            if (eff > best) { best = eff; k = t; }
+        }
+    }
+    const uint32_t chunk = (uint32_t)std::min<uint64_t>(65536, (ncode + k - 1) / k);
     const uint64_t nchunks = (ncode + chunk - 1) / chunk;
     const uint64_t items = nchunks * groups;
-    const uint32_t per = std::min<uint32_t>(groups, (uint32_t)c->num_sms);
     for (uint64_t it = 0; it < items;) {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(per, items - it);
         c->eng->vm2(c->stream, blocks, state2, cap2, tab, d_code, ncode, chunk, groups, it, inv_fail);
@@ -637,12 +678,25 @@ static int run_program(ecm_b200_ctx *c, const std::vector<uint64_t> &host_code, 
                 int rc = run_vm2(c, d_code + seg, i - seg, state2, cap2, tab, groups, inv_fail);
                 if (rc) return rc;
                 {   // chunk-major (group, chunk) items, at most one resident wave per launch
+                    S2Mark mark(c, 1);
                     const uint32_t TP = (uint32_t)c->eng->threads_pair, npairs = (uint32_t)(j - i);
+                    const uint32_t pgroups = (ncurves + TP - 1) / TP;
+                    const uint32_t per = std::min<uint32_t>(pgroups, (uint32_t)(c->num_sms * c->eng->pair_blocks_per_sm));
+                    // chunk length: the split of the run into k chunks whose k * pgroups items leave the fewest block slots of
+                    // the last launch empty, each chunk paying about two products (accumulator reload, re-join of the halves)
                     uint32_t pchunk = 512;
                     if (const char *e = getenv("ECM_B200_PAIR_CHUNK")) { const int v = atoi(e); if (v >= 16) pchunk = (uint32_t)v; }
-                    const uint32_t pgroups = (ncurves + TP - 1) / TP;
+                    else if (pgroups > per || npairs > 512) {
+                        double best = 0;
+                        const uint32_t kmin = (npairs + 1023) / 1024, kmax = std::max<uint32_t>(kmin, npairs / 96);
+                        for (uint32_t k = kmin; k <= kmax && k < kmin + 64; k++) {
+                            const uint32_t len = (npairs + k - 1) / k;
+                            const uint64_t it = (uint64_t)((npairs + len - 1) / len) * pgroups, launches = (it + per - 1) / per;
+                            const double eff = (double)it / (double)(launches * per) * (double)len / (double)(len + 2);
+                            if (eff > best) { best = eff; pchunk = len; }
+                        }
+                    }
                     const uint64_t items = (uint64_t)((npairs + pchunk - 1) / pchunk) * pgroups;
-                    const uint32_t per = std::min<uint32_t>(pgroups, (uint32_t)(c->num_sms * c->eng->pair_blocks_per_sm));
                     for (uint64_t it = 0; it < items;) {
                         const uint32_t blocks = (uint32_t)std::min<uint64_t>(per, items - it);
                         c->eng->pair_run(c->stream, blocks, state2, cap2, tab, d_code + i, npairs, ncurves, pchunk, pgroups, it);
@@ -805,6 +859,7 @@ int ecm_b200_stage2(ecm_b200_ctx *c, uint64_t b1, uint64_t b2)
     CU(cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->s2_ms, c->ev0, c->ev1);
     c->last_ms = c->s2_ms; c->last_launches = c->s2_launches;
+    s2_trace_report(c, "stage2");
     c->stage2_done = true;
     return ECM_B200_OK;
 }
@@ -833,6 +888,7 @@ int ecm_b200_stage2_init(ecm_b200_ctx *c, uint64_t b1, int *found_inv)
     CU(cudaMemcpyAsync(fl.data(), c->d_fail, c->count, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->s2_ms += ms; c->last_ms = ms; c->last_launches = c->s2_launches;
+    s2_trace_report(c, "stage2_init");
     if (found_inv) { *found_inv = 0; for (uint8_t f : fl) if (f) { *found_inv = 1; break; } }
     c->s2_open = true; c->stage2_done = true;
     return ECM_B200_OK;
@@ -858,6 +914,7 @@ int ecm_b200_stage2_range(ecm_b200_ctx *c, uint32_t amin, const uint32_t *pm_v, 
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->s2_ms += ms; c->last_ms = ms; c->last_launches = c->s2_launches - before;
+    s2_trace_report(c, "stage2_range");
     return ECM_B200_OK;
 }
 

@@ -604,8 +604,8 @@ def main():
             also["config2_1024bit"] = config_sample(E, "syn1024", 3000000, curves, 32768, 3, 2000000, peak_prod, local_rank, (5000, 300000))
         except Exception as e:          # a side measurement must never take the headline line down
             also["config2_1024bit"] = {"error": repr(e)}
-        try:    # [4] 2048-bit, B1 = 1.1e7: one resident wave of the four-lanes-per-curve kernel
-            also["config4_2048bit"] = config_sample(E, "syn2048", 11000000, 14208, 4736, 3, 1000000, peak_prod, local_rank, (2000, 60000))
+        try:    # [4] 2048-bit, B1 = 1.1e7: one resident wave of the four-lanes-per-curve kernels (148 blocks x 96 curves), both stages
+            also["config4_2048bit"] = config_sample(E, "syn2048", 11000000, 14208, 14208, 3, 1000000, peak_prod, local_rank, (2000, 60000))
         except Exception as e:
             also["config4_2048bit"] = {"error": repr(e)}
         # stage-2 sample on the bench composite: B1=1e5 -> B2=1e7 (D=2310, U=16), all curves of this GPU
