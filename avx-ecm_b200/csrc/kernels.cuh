@@ -389,16 +389,18 @@ __device__ __noinline__ void vm2_inverse(uint32_t *dptr, const uint32_t *xptr, u
     for (int k = 0; k < NL; k++) dptr[k * STRIDE] = t[k];
 }
 
-// Block geometry of the stage-2 machine.  Up to 32 limbs the slot file is hybrid like stage 1's (the three
-// work points and the accumulator stay in the L2-resident state, 7 scratch slots in shared memory), which
-// doubles the resident warps at 1024 bits (128 -> 256 threads); wider moduli keep all 14 slots in shared.
+// Block geometry of the stage-2 machine.  The slot file is hybrid like stage 1's (the three work points and the
+// accumulator stay in the L2-resident state, 7 scratch slots in shared memory), which buys resident warps: 128 -> 256
+// threads per SM at 1024 bits (+21 %), 256 -> 384 at 13 limbs; wider moduli keep all 14 slots in shared.
 template <int NL>
 struct S2Cfg {
-    // measured: +21 % at 32 limbs (128 -> 256 threads per SM), -3 % at 13 limbs where 256 threads fit anyway
+    // 13 limbs, stage 2 at B1=1e6/B2=1e8 with 65 536 curves: with one chunk per segment the 171 groups of 384 left the
+    // second launch of every segment 85 % empty and the hybrid file lost (12.6 s against 11.9 s); with run_vm2() cutting
+    // segments into chunks that fill the launches it wins (slot-machine segments 2.95 -> 2.69 s, stage 2 11.43 -> 11.17 s)
 #ifndef ECM_S2_HYBRID_SMALL
-#define ECM_S2_HYBRID_SMALL 0
+#define ECM_S2_HYBRID_SMALL 1
 #endif
-    static constexpr bool HYBRID = (NL >= 20 && NL <= 32) || (ECM_S2_HYBRID_SMALL && NL <= 16 /* tried at 13 limbs: 12.6 s against 11.9 s for stage 2 at B1=1e6/B2=1e8 */);
+    static constexpr bool HYBRID = (NL >= 20 && NL <= 32) || (ECM_S2_HYBRID_SMALL && NL <= 16);
     static constexpr int nsmem = HYBRID ? (NSLOT_S2 - NGLOBAL_S2) : NSLOT_S2;
     static constexpr int per_thread = nsmem * NL * 4;
     static constexpr int fit = (kSmemBudget / per_thread) / 32 * 32;

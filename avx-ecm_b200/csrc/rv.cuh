@@ -39,6 +39,20 @@ struct SoloField {
         if (NL <= 16) mont_mul2<NL>(a0, a0, b0, a1, a1, b1, P);
         else { mont_mul<NL>(a0, a0, b0, P); mont_mul<NL>(a1, a1, b1, P); }
     }
+    // (a0, a1) <- (a0^2, a1^2): the dedicated dual squaring (1.5n^2+2.5n products each) where it is compiled in
+#ifndef ECM_RV_SQR
+#define ECM_RV_SQR 0
+#endif
+    static constexpr bool HAS_SQR2 = ECM_RV_SQR && !ECM_SPECIAL && NL <= 16 && NL >= 4;
+    __device__ __forceinline__ void sqr2(uint32_t (&a0)[M], uint32_t (&a1)[M]) const
+    {
+        uint32_t aa[2][NL], rr[2][NL];
+#pragma unroll
+        for (int k = 0; k < NL; k++) { aa[0][k] = a0[k]; aa[1][k] = a1[k]; }
+        mont_sqr_k<NL, 2>(rr, aa, P);
+#pragma unroll
+        for (int k = 0; k < NL; k++) { a0[k] = rr[0][k]; a1[k] = rr[1][k]; }
+    }
     __device__ __forceinline__ void mul(uint32_t (&a)[M], const uint32_t (&b)[M]) const { mont_mul<NL>(a, a, b, P); }
     __device__ __forceinline__ void add(uint32_t (&r)[M], const uint32_t (&a)[M], const uint32_t (&b)[M]) const { mod_add<NL>(r, a, b, P); }
     __device__ __forceinline__ void sub(uint32_t (&r)[M], const uint32_t (&a)[M], const uint32_t (&b)[M]) const { mod_sub<NL>(r, a, b, P); }
@@ -50,6 +64,8 @@ struct CoopField {
     uint32_t n[M];
     uint32_t m0inv;
     coop::WarpComm<L> cm;
+    static constexpr bool HAS_SQR2 = false;
+    __device__ __forceinline__ void sqr2(uint32_t (&)[M], uint32_t (&)[M]) const {}
     __device__ __forceinline__ explicit CoopField(const ModParams<LIMBS> &p)
     {
         m0inv = p.m0inv;
@@ -157,9 +173,33 @@ k_stage1_rv(const ModParams<F::LIMBS> P, uint32_t *__restrict__ state, const uin
                 rv_store<M, STRIDE>(py, A0); rv_store<M, STRIDE>(py + SLOTW, A1);
                 continue;
             }
-            if (kind == PH_D3) {
+            if constexpr (F::L > 1) {
+                // one body of the cooperative product in the kernel, looped once (D3) or twice with the operand pairs
+                // swapped in between: three inlined copies (5 120 SASS instructions) stalled every fourth issue slot on
+                // instruction fetch once all 148 SMs ran the kernel (ncu: no_instruction 1.13 per issue)
+                const int np = (kind == PH_D3) ? 1 : 2;
+                if (kind == PH_D3) {
+#pragma unroll
+                    for (int j = 0; j < M; j++) B0[j] = B1[j];
+                }
+#pragma unroll 1
+                for (int h = 0; h < np; h++) {
+                    field.mul(A0, B0);
+                    if (np == 2) {
+#pragma unroll
+                        for (int j = 0; j < M; j++) {
+                            uint32_t t = A0[j]; A0[j] = A1[j]; A1[j] = t;
+                            t = B0[j]; B0[j] = B1[j]; B1[j] = t;
+                        }
+                    }
+                }
+                if (kind == PH_D3) rv_store<M, STRIDE>(px + SLOTW, A0);
+                else if (kind == PH_A3) { rv_store<M, STRIDE>(py, A0); rv_store<M, STRIDE>(py + SLOTW, A1); }
+            } else if (kind == PH_D3) {
                 field.mul(A0, B1);
                 rv_store<M, STRIDE>(px + SLOTW, A0);
+            } else if (F::HAS_SQR2 && (kind == PH_A2 || kind == PH_D1L || kind == PH_D1P)) {
+                field.sqr2(A0, A1);
             } else {
                 field.mul2(A0, B0, A1, B1);
                 if (kind == PH_A3) { rv_store<M, STRIDE>(py, A0); rv_store<M, STRIDE>(py + SLOTW, A1); }
