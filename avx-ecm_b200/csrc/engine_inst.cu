@@ -29,13 +29,21 @@ template <int NL> struct RvCfg<NL, typename std::enable_if<(NL <= RV_SOLO_MAX)>:
     typedef SoloField<NL> Field;
 };
 #if !ECM_SPECIAL
+template <> struct RvCfg<40> { static constexpr int MAXT = 384, BIG = 0; typedef CoopField<10, 4> Field; };
 template <> struct RvCfg<48> { static constexpr int MAXT = 384, BIG = 0; typedef CoopField<12, 4> Field; };
+template <> struct RvCfg<56> { static constexpr int MAXT = 384, BIG = 0; typedef CoopField<14, 4> Field; };
 template <> struct RvCfg<64> { static constexpr int MAXT = 384, BIG = 0; typedef CoopField<16, 4> Field; };
 #endif
 // stage 2 on the cooperative layout (coop_s2.cuh) where stage 1 has it
 template <int NL> struct S2CoopCfg { static constexpr int M = 0, L = 1; };
 #if !ECM_SPECIAL
+// 28 / 32 limbs: TWO lanes per curve in stage 2 only -- a wave is limited by the tables (3 MB per curve at 1024 bits: 32 768
+// curves in 98 GB), which leaves one thread per curve with 7 warps per SM
+template <> struct S2CoopCfg<28> { static constexpr int M = 14, L = 2; };
+template <> struct S2CoopCfg<32> { static constexpr int M = 16, L = 2; };
+template <> struct S2CoopCfg<40> { static constexpr int M = 10, L = 4; };
 template <> struct S2CoopCfg<48> { static constexpr int M = 12, L = 4; };
+template <> struct S2CoopCfg<56> { static constexpr int M = 14, L = 4; };
 template <> struct S2CoopCfg<64> { static constexpr int M = 16, L = 4; };
 #endif
 template <class F> struct RvLanes { static constexpr int L = F::L, M = F::M; };

@@ -94,7 +94,7 @@ int main()
         const Big a = parse(ah, n), b = parse(bh, n), N = parse(nh, n);
         Big r;
 #define CASE(m, l) if (M == m && L == l) r = run<m, l>(op, a, b, N);
-        CASE(16, 4) CASE(12, 4) CASE(16, 2) CASE(8, 4) CASE(2, 2) CASE(4, 8) CASE(2, 4) CASE(10, 2) CASE(16, 8)
+        CASE(16, 4) CASE(14, 4) CASE(12, 4) CASE(10, 4) CASE(16, 2) CASE(8, 4) CASE(2, 2) CASE(4, 8) CASE(2, 4) CASE(10, 2) CASE(16, 8)
 #undef CASE
         if (r.empty()) { printf("unsupported\n"); continue; }
         for (int k = n - 1; k >= 0; k--) printf("%08x", r[k]);

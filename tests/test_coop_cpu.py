@@ -47,7 +47,7 @@ def moduli(rng, bits):
             (1 << (bits - 31)) - 1]
 
 
-@pytest.mark.parametrize("M,L", [(16, 4), (12, 4), (16, 2), (8, 4), (2, 2), (4, 8), (2, 4), (10, 2), (16, 8)])
+@pytest.mark.parametrize("M,L", [(16, 4), (14, 4), (12, 4), (10, 4), (16, 2), (8, 4), (2, 2), (4, 8), (2, 4), (10, 2), (16, 8)])
 def test_coop_field_ops_match_python(harness, M, L):
     rng = random.Random(1000 * M + L)
     bits = 32 * M * L

@@ -261,12 +261,13 @@ def test_gpu_lines_are_valid_gmp_ecm_resume_points():
 
 @pytest.mark.parametrize("name,curves,b1", [("small96", 70, 3000), ("syn206", 70, 3000), ("t35", 200, 3000), ("syn415", 500, 5000),
                                             ("readme508", 200, 3000), ("csh_line19", 100, 3000), ("csh_line02", 100, 3000),
-                                            ("slow_csh_line07", 100, 1500), ("syn2048", 150, 1000)])
+                                            ("slow_csh_line07", 100, 1500), ("syn2048", 150, 1000), ("syn880", 100, 2000),
+                                            ("syn1250", 100, 1500), ("syn1750", 100, 1000)])
 def test_register_machine_and_slot_machine_kernels_agree(name, curves, b1, monkeypatch):
     """Stage 1 has two kernel generations: the slot-file machine (vm.cuh, one thread per curve) and the register-resident
     macro-op machine (rv.cuh) -- one thread per curve up to 16 limbs, FOUR LANES per curve (warp-cooperative limbs,
     coop.cuh) at 48 and 64 limbs.  Same op stream, different state layouts and arithmetic routines: every residue of every
-    curve must be identical, and equal to the oracle's (3, 7, 10, 13, 16, 20, 24, 48 and 64 limbs)."""
+    curve must be identical, and equal to the oracle's (3, 7, 10, 13, 16, 20, 24, 28, 40, 48, 56 and 64 limbs)."""
     N = composites()[name] if name in composites() else int(GOLDEN[name]["n"])
     sig = [1000 + 3 * i for i in range(curves)]
     res = {}

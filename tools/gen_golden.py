@@ -81,6 +81,10 @@ def composites():
         "small96": 1000000007 * 998244353 * 4294967311,   # tiny composite: exercises factor/inversion-failure paths
         "csh150m": 19223719229397103735869895564468606263251785680561653388554202432164204897138631706690937388406707574740021324772129,
         "syn206": synthetic(103, 103, 12348),     # 206 bits: the reference's smallest word count, for the B1 > 1e8 case
+        # sizes that land in the in-between kernel sets (28 limbs one thread per curve; 40 and 56 limbs four lanes per curve)
+        "syn880": synthetic(440, 440, 12349),
+        "syn1250": synthetic(625, 625, 12350),
+        "syn1750": synthetic(875, 875, 12351),
     }
 
 
@@ -120,6 +124,9 @@ def cases():
         ("syn415_b1_3e4_s1only", c["syn415"], 16, 30000, 30000, 100),
         ("syn1024_b1_2e4", c["syn1024"], 8, 20000, 2000000, 7),
         ("syn2048_b1_5e3", c["syn2048"], 8, 5000, 500000, 7),
+        ("syn880_b1_2e4", c["syn880"], 8, 20000, 2000000, 7),
+        ("syn1250_b1_1e4", c["syn1250"], 8, 10000, 1000000, 7),
+        ("syn1750_b1_5e3", c["syn1750"], 8, 5000, 500000, 7),
         ("csh250k_stage1_factor", c["csh250k"], 8, 250000, 250000, 3462348953),
         ("csh1m_stage1_factor", c["csh1m"], 8, 1000000, 1000000, 7372562557),
         ("t35_stage2_factor", c["t35"], 8, 1000000, 100000000, 416265588),
