@@ -37,10 +37,9 @@ template <> struct RvCfg<64> { static constexpr int MAXT = 384, BIG = 0; typedef
 // stage 2 on the cooperative layout (coop_s2.cuh) where stage 1 has it
 template <int NL> struct S2CoopCfg { static constexpr int M = 0, L = 1; };
 #if !ECM_SPECIAL
-// 28 / 32 limbs: TWO lanes per curve in stage 2 only -- a wave is limited by the tables (3 MB per curve at 1024 bits: 32 768
-// curves in 98 GB), which leaves one thread per curve with 7 warps per SM
-template <> struct S2CoopCfg<28> { static constexpr int M = 14, L = 2; };
-template <> struct S2CoopCfg<32> { static constexpr int M = 16, L = 2; };
+// (28 / 32 limbs with TWO lanes per curve in stage 2 -- a wave is limited by the tables, 32 768 curves at 1024 bits, which leaves
+// one thread per curve with 7 warps per SM -- was measured and lost: pair runs 5.27 s either way, slot machine 3.29 -> 4.56 s,
+// profiles/r2o_s2_1024_*.log)
 template <> struct S2CoopCfg<40> { static constexpr int M = 10, L = 4; };
 template <> struct S2CoopCfg<48> { static constexpr int M = 12, L = 4; };
 template <> struct S2CoopCfg<56> { static constexpr int M = 14, L = 4; };

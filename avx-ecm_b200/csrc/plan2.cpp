@@ -89,9 +89,13 @@ void ladder(Asm &a, const Stage2Layout &L, uint64_t c, uint64_t &ptadds)
 
 // Montgomery's simultaneous inversion (batch_invert_pt_*, ecm.c:1869-2136) over table entries
 // zs[0..n): out[i] = x[i] / z[i].  Prefix products go to the table `pref`; the running suffix
-// inverse lives in slot T1.
+// inverse lives in slot T1.  `scratch` is one more dead slot.
+// Back-substitution computes three products per entry -- 1/z[i] = B[i]*A[i-1], B[i-1] = z[i]*B[i], out[i] = x[i]/z[i] --
+// and the third depends on the first.  Entry by entry that is a dual product plus a single one (half the carry chains in
+// flight); taken two entries at a time the six products pair up as (1/z[i], B[i-1]), (out[i], 1/z[i-1]), (B[i-2], out[i-1]):
+// the same products with the same operands, hence the same table contents, in three dual instructions.
 void batch_invert(Asm &a, const std::vector<uint32_t> &xs, const std::vector<uint32_t> &zs,
-                  const std::vector<uint32_t> &outs, uint32_t pref)
+                  const std::vector<uint32_t> &outs, uint32_t pref, uint32_t scratch)
 {
     const size_t n = zs.size();
     a.ldg(T1_, zs[0]);
@@ -102,13 +106,27 @@ void batch_invert(Asm &a, const std::vector<uint32_t> &xs, const std::vector<uin
         a.stg(T1_, pref + (uint32_t)i);
     }
     a.inv(T1_, T1_);                               // B[n-1]
-    for (size_t i = n - 1; i >= 1; i--) {
+    size_t i = n - 1;
+    for (; i >= 2; i -= 2) {
         a.ldg(T2_, pref + (uint32_t)i - 1);
         a.ldg(D1_, zs[i]);
-        a.mul2(T2_, T1_, T2_, T1_, D1_, T1_);      // 1/z[i] = B[i] * A[i-1]   |   B[i-1] = z[i] * B[i]
+        a.mul2(T2_, T1_, T2_, T1_, D1_, T1_);      // 1/z[i] = B[i] * A[i-1]        |   B[i-1] = z[i] * B[i]
         a.ldg(S1_, xs[i]);
-        a.mul(S1_, S1_, T2_);
+        a.ldg(scratch, pref + (uint32_t)i - 2);
+        a.mul2(S1_, S1_, T2_, scratch, T1_, scratch);   // out[i] = x[i] / z[i]     |   1/z[i-1] = B[i-1] * A[i-2]
         a.stg(S1_, outs[i]);
+        a.ldg(D1_, zs[i - 1]);
+        a.ldg(S1_, xs[i - 1]);
+        a.mul2(T1_, D1_, T1_, S1_, S1_, scratch);  // B[i-2] = z[i-1] * B[i-1]     |   out[i-1] = x[i-1] / z[i-1]
+        a.stg(S1_, outs[i - 1]);
+    }
+    if (i == 1) {
+        a.ldg(T2_, pref);
+        a.ldg(D1_, zs[1]);
+        a.mul2(T2_, T1_, T2_, T1_, D1_, T1_);
+        a.ldg(S1_, xs[1]);
+        a.mul(S1_, S1_, T2_);
+        a.stg(S1_, outs[1]);
     }
     a.ldg(S1_, xs[0]);
     a.mul(S1_, S1_, T1_);
@@ -171,7 +189,7 @@ void plan_stage2_init(uint64_t b1, Stage2Program &prog)
     {
         std::vector<uint32_t> xs, zs;
         for (uint32_t i = 1; i <= last; i++) { xs.push_back(L.pbx + i); zs.push_back(L.pbz + i); }
-        batch_invert(a, xs, zs, xs, L.pba);
+        batch_invert(a, xs, zs, xs, L.pba, WX);      // all three work points are dead here (the ladder below reloads Q)
         prog.numinv++;
     }
     // Pd = [w]Q
@@ -246,7 +264,7 @@ void plan_stage2_pairmap(uint32_t amin, const uint32_t *pm_v, const uint32_t *pm
     auto invert = [&](uint32_t from, uint32_t to) {
         std::vector<uint32_t> xs, zs, outs;
         for (uint32_t i = from; i < to; i++) { xs.push_back(L.pax + ring(i)); zs.push_back(L.paz + ring(i)); outs.push_back(L.pai + ring(i)); }
-        batch_invert(a, xs, zs, outs, L.paa);
+        batch_invert(a, xs, zs, outs, L.paa, out.x);  // `out` is the one work point the chain does not need any more
         prog.numinv++;
     };
     for (uint32_t i = 2; i < win; i++) extend(i);

@@ -57,11 +57,16 @@ PROFILE_SUMMARY = "profiles/r2_final_stage1_ncu_full_summary.txt"
 
 
 def profile_traffic():
+    """DRAM bytes per launch of the headline kernel, read from the committed `ncu --set full` summary (ncu prints the unit
+    it likes per metric); None when the summary is absent."""
     try:
         txt = open(os.path.join(ROOT, PROFILE_SUMMARY)).read()
-        rd = float(re.search(r"dram__bytes_read.sum \[Mbyte\] = ([0-9.]+)", txt).group(1))
-        wr = float(re.search(r"dram__bytes_write.sum \[Mbyte\] = ([0-9.]+)", txt).group(1))
-        return int((rd + wr) * 1e6)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(re.escape(name) + r" \[(\w+)\] = ([0-9.]+)", txt)
+            total += float(m.group(2)) * scale[m.group(1)]
+        return int(total)
     except Exception:
         return None
 
