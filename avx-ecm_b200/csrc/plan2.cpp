@@ -95,15 +95,17 @@ void ladder(Asm &a, const Stage2Layout &L, uint64_t c, uint64_t &ptadds)
 // flight); taken two entries at a time the six products pair up as (1/z[i], B[i-1]), (out[i], 1/z[i-1]), (B[i-2], out[i-1]):
 // the same products with the same operands, hence the same table contents, in three dual instructions.
 void batch_invert(Asm &a, const std::vector<uint32_t> &xs, const std::vector<uint32_t> &zs,
-                  const std::vector<uint32_t> &outs, uint32_t pref, uint32_t scratch)
+                  const std::vector<uint32_t> &outs, uint32_t pref, uint32_t scratch, bool prefix_done = false)
 {
     const size_t n = zs.size();
-    a.ldg(T1_, zs[0]);
-    a.stg(T1_, pref);
-    for (size_t i = 1; i < n; i++) {               // A[i] = z[i] * A[i-1]
-        a.ldg(T2_, zs[i]);
-        a.mul(T1_, T2_, T1_);
-        a.stg(T1_, pref + (uint32_t)i);
+    if (!prefix_done) {                            // else the caller has A[0..n) in the table and A[n-1] in T1
+        a.ldg(T1_, zs[0]);
+        a.stg(T1_, pref);
+        for (size_t i = 1; i < n; i++) {           // A[i] = z[i] * A[i-1]
+            a.ldg(T2_, zs[i]);
+            a.mul(T1_, T2_, T1_);
+            a.stg(T1_, pref + (uint32_t)i);
+        }
     }
     a.inv(T1_, T1_);                               // B[n-1]
     size_t i = n - 1;
@@ -254,9 +256,33 @@ void plan_stage2_pairmap(uint32_t amin, const uint32_t *pm_v, const uint32_t *pm
     a.stpt(PU, L.pax + ring(1), L.paz + ring(1));
     // chain: cur = Pa[i-1] (U), prev = Pa[i-2] (V), out (W)
     Pt cur = PU, prev = PV, out = PW;
+    // Window points are extended and inverted in runs: the Z coordinates of the run go through Montgomery's simultaneous
+    // inversion, whose prefix products A[r] = z[r] * A[r-1] are a serial chain of SINGLE products (one carry-chain pair in
+    // flight per thread, and a table load in front of each: measured 11 us per product against 6.8 us per dual product in
+    // the window-shift launches).  The chain only needs z[r], which sits in a work-point slot for two extensions after
+    // point r was made, so the last dual product of every second extension is split and takes two prefix products along:
+    // (out.x, A[r-2]) and (out.z, A[r-1]) instead of (out.x, out.z) -- same products, same operands, same table contents.
+    uint32_t pf_from = 0, pf_done = 0;             // run of entries being inverted: first ring index, prefix products made
     auto extend = [&](uint32_t i) {
         a.sums1(cur);
-        a.vadd(prev, out);
+        const uint32_t r = i - pf_from;            // entries pf_from .. i-1 exist; prev = entry i-2, cur = entry i-1
+        if (r >= 2 && r - pf_done == 2) {
+            a.mul2(D1_, D1_, S2_, S1_, S1_, D2_);  // vadd (ecm.c:407-443) with its last dual product split
+            a.addsub(D1_, S1_, D1_, S1_);
+            a.mul2(D1_, D1_, D1_, S1_, S1_, S1_);
+            if (pf_done == 0) {
+                a.copy(T1_, prev.z);               // A[0] = z[0]
+                a.mul2(out.x, D1_, prev.z, out.z, S1_, prev.x);
+            } else {
+                a.mul2(out.x, D1_, prev.z, T1_, prev.z, T1_);
+            }
+            a.stg(T1_, L.paa + pf_done++);
+            if (pf_done == 1) a.mul(T1_, cur.z, T1_);
+            else a.mul2(out.z, S1_, prev.x, T1_, cur.z, T1_);
+            a.stg(T1_, L.paa + pf_done++);
+        } else {
+            a.vadd(prev, out);
+        }
         prog.ptadds++;
         a.stpt(out, L.pax + ring(i), L.paz + ring(i));
         Pt t = prev; prev = cur; cur = out; out = t;
@@ -264,7 +290,17 @@ void plan_stage2_pairmap(uint32_t amin, const uint32_t *pm_v, const uint32_t *pm
     auto invert = [&](uint32_t from, uint32_t to) {
         std::vector<uint32_t> xs, zs, outs;
         for (uint32_t i = from; i < to; i++) { xs.push_back(L.pax + ring(i)); zs.push_back(L.paz + ring(i)); outs.push_back(L.pai + ring(i)); }
-        batch_invert(a, xs, zs, outs, L.paa, out.x);  // `out` is the one work point the chain does not need any more
+        // the prefix products the extensions could not take along: entries to-2 (prev) and to-1 (cur)
+        const uint32_t n = to - from;
+        bool done = false;
+        if (pf_from == from && n >= 2 && pf_done == n - 2) {
+            if (pf_done == 0) a.copy(T1_, prev.z); else a.mul(T1_, prev.z, T1_);
+            a.stg(T1_, L.paa + pf_done++);
+            a.mul(T1_, cur.z, T1_);
+            a.stg(T1_, L.paa + pf_done++);
+            done = true;
+        }
+        batch_invert(a, xs, zs, outs, L.paa, out.x, done);   // `out` is the one work point the chain does not need any more
         prog.numinv++;
     };
     for (uint32_t i = 2; i < win; i++) extend(i);
@@ -274,6 +310,7 @@ void plan_stage2_pairmap(uint32_t amin, const uint32_t *pm_v, const uint32_t *pm
     for (uint32_t k = 0; k < steps; k++) {
         if (pm_u[k] == 0 && pm_v[k] == 0) {        // slide the window by 2U points (ecm.c:2458-2502)
             base = (base + 2 * U) % win;
+            pf_from = win - 2 * U; pf_done = 0;
             for (uint32_t i = win - 2 * U; i < win; i++) extend(i);
             amin += U;
             invert(win - 2 * U, win);

@@ -1,0 +1,8 @@
+set -x
+cd /root/repo
+( time timeout 900 python -m pytest tests/test_gpu_stage2.py -m gpu -x -q ) > gpurun_out/r2s_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2s_tests.log
+tail -4 gpurun_out/r2s_tests.log
+ECM_B200_S2_TRACE=1 timeout 300 python tools/perf_probe3.py syn415 65536 1000000 100000000 > gpurun_out/r2s_s2_415.log 2>&1
+ECM_B200_S2_TRACE=1 timeout 300 python tools/perf_probe3.py syn1024 32768 3000000 20000000 > gpurun_out/r2s_s2_1024.log 2>&1
+ECM_B200_S2_TRACE=1 timeout 300 python tools/perf_probe3.py syn2048 14208 11000000 20000000 > gpurun_out/r2s_s2_2048.log 2>&1
+tail -n2 gpurun_out/r2s_s2_*.log
