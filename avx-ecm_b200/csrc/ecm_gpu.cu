@@ -282,7 +282,12 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
     // occupancy by the launch schedule.  Pick the block size that maximises the product.
     {
         const uint32_t Lc = eng->use_rv ? (uint32_t)eng->rv_lanes : 1u;        // lanes per curve
-        const uint32_t S = eng->use_rv ? (uint32_t)eng->rv_max_threads : (uint32_t)eng->stride_s1, sms = (uint32_t)c->num_sms;
+        uint32_t S = eng->use_rv ? (uint32_t)eng->rv_max_threads : (uint32_t)eng->stride_s1;
+        const uint32_t sms = (uint32_t)c->num_sms;
+        // one thread per curve from 20 limbs up: 8 warps per SM beat 12 whatever the machine (65 536 curves, Tprod/s at 256
+        // against 384 threads: 7.98 / 7.81 at 20 limbs, 7.65 / 7.47 at 24, 8.09 / 6.80 at 28 -- profiles/r2v_s1_*.log), which
+        // the warps-hide-latency model below does not know
+        if (Lc == 1 && nl >= 20 && S > 256) S = 256;
         // the fold kernels (half the IMADs per product, same loads and carry chains) are bound by dependent-issue
         // latency: measured 67.0k -> 72.8k curves/s from 12 to 16 warps even with 20 of 148 SMs left idle
         const double lat = fold ? 40.0 : 3.6;
