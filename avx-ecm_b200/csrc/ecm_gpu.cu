@@ -287,7 +287,7 @@ static int create_ctx(ecm_b200_ctx **out, int device, const uint32_t *n, int nli
         // one thread per curve from 20 limbs up: 8 warps per SM beat 12 whatever the machine (65 536 curves, Tprod/s at 256
         // against 384 threads: 7.98 / 7.81 at 20 limbs, 7.65 / 7.47 at 24, 8.09 / 6.80 at 28 -- profiles/r2v_s1_*.log), which
         // the warps-hide-latency model below does not know
-        if (Lc == 1 && nl >= 20 && S > 256) S = 256;
+        if (!fold && Lc == 1 && nl >= 20 && S > 256) S = 256;
         // the fold kernels (half the IMADs per product, same loads and carry chains) are bound by dependent-issue
         // latency: measured 67.0k -> 72.8k curves/s from 12 to 16 warps even with 20 of 148 SMs left idle
         const double lat = fold ? 40.0 : 3.6;
