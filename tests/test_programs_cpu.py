@@ -151,7 +151,10 @@ def run_stage2_program(N, code, slots, tab):
             raise AssertionError("unknown op %d" % op)
 
 
-@pytest.mark.parametrize("name,b1,b2,sigma", [("syn415", 300, 20000, 7), ("t35", 5000, 120000, 99), ("syn415", 50, 3000, 11)])
+@pytest.mark.parametrize("name,b1,b2,sigma", [("syn415", 300, 20000, 7), ("t35", 5000, 120000, 99), ("syn415", 50, 3000, 11),
+                                              # every D the planner selects (30 ... 2310), several window shifts each
+                                              ("syn206", 100, 10000, 13), ("syn206", 200, 20000, 14), ("syn206", 400, 40000, 15),
+                                              ("syn206", 1500, 150000, 16), ("syn206", 3000, 300000, 17), ("syn206", 20000, 600000, 18)])
 def test_stage2_program_reproduces_oracle_accumulator(name, b1, b2, sigma):
     N = composites()[name]
     o = O.ecm_curve(N, b1, b2, sigma)
