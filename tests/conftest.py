@@ -41,7 +41,7 @@ def is_known_answer(name):
 
 
 # test.csh lines whose 8 curves keep one warp busy for 1.5-4 minutes (B1 = 3e6, B2 up to 1e9, 24-limb inputs): with the
-# "slow_" cases they run under ECM_B200_SLOW=1 (log of such a run on the GPU: profiles/r2_known_answers_all.log)
+# "slow_" cases they run under ECM_B200_SLOW=1 (log of such a run on the GPU: profiles/r2_final_known_answers_all.log)
 HEAVY = ("csh_line02", "csh_line09", "csh_line11", "csh_line14", "csh_line22", "csh_line25")
 
 
